@@ -1,0 +1,136 @@
+/*
+ * mpgnn_b200 -- C ABI of the B200-native MPGNN hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch types),
+ * runs on the CUDA stream passed as `stream` (a cudaStream_t cast to void*), performs no
+ * hidden device synchronisation unless stated, and returns 0 on success or a negative
+ * MPGNN_E* code; the message is available from mpgnn_last_error() (thread local).
+ * Pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference repository root).  Orientation: edge_index row 0 is the aggregation TARGET
+ * (CSR row), row 1 the message SOURCE (CSR column) -- every reference conv is built
+ * with flow='target_to_source' (model.py:190,192).
+ */
+#ifndef MPGNN_B200_H
+#define MPGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPGNN_OK 0
+#define MPGNN_EINVAL (-1)   /* bad argument (maps to ValueError in the Python host)      */
+#define MPGNN_ECUDA (-2)    /* CUDA runtime error (RuntimeError)                          */
+#define MPGNN_ERANGE (-3)   /* node id / relation id outside [0,N) / [0,R) (ValueError)   */
+#define MPGNN_ENOTSUP (-4)  /* size outside what the kernels support (NotImplementedError) */
+
+/* epilogue flags of mpgnn_hop_fwd / mpgnn_hop_bwd */
+#define MPGNN_F_RELU 1u         /* y = relu(z)                 (model.py:210,213)            */
+#define MPGNN_F_DROPOUT_SEED 2u /* keep-mask from the counter RNG (seed, offset)             */
+#define MPGNN_F_DROPOUT_MASK 4u /* keep-mask supplied bit-packed, np.packbits(axis=1) layout */
+#define MPGNN_F_NEED_GX 8u      /* bwd: also produce the input gradient (hidden layers)      */
+#define MPGNN_F_TF32X3 16u      /* projection on tcgen05 with the 3xTF32 split (fp32 parity) */
+#define MPGNN_F_BF16 32u        /* projection on tcgen05 in bf16 (stated tolerance)          */
+
+typedef struct mpgnn_graph mpgnn_graph; /* relation-typed CSR + CSC, device resident */
+
+const char* mpgnn_last_error(void);
+int mpgnn_abi_version(void);
+
+/* ---- K1: relation-typed CSR/CSC construction ------------------------------------------
+ * Replaces the per-call O(E) filter `masked_edge_index(edge_index, edge_type == relation)`
+ * (mp_rgcn_layer.py:29-37, call site :231) and the scatter index PyG derives from it:
+ * edges are bucketed ONCE by (relation,row) and by (relation,col) with a stable LSD radix
+ * sort, so bucket (r,i) lists its edges in the original edge order, duplicates kept --
+ * bit-exact with what the reference enumerates.  Synchronises the stream once at the end
+ * (range check).  d_edge_index is int64 [2,E] row-major, d_edge_type int64 [E]. */
+int mpgnn_graph_build(const int64_t* d_edge_index, const int64_t* d_edge_type, int64_t num_edges,
+                      int64_t num_nodes, int64_t num_relations, void* stream, mpgnn_graph** out);
+/* Same with HOST buffers (the reference-facing form: main.py:366-372 builds them on the
+ * host); the host->device copies are part of the call. */
+int mpgnn_graph_build_host(const int64_t* h_edge_index, const int64_t* h_edge_type, int64_t num_edges,
+                           int64_t num_nodes, int64_t num_relations, void* stream, mpgnn_graph** out);
+void mpgnn_graph_free(mpgnn_graph* g);
+int mpgnn_graph_info(const mpgnn_graph* g, int64_t* num_nodes, int64_t* num_edges, int64_t* num_relations);
+/* Device views of one relation: ptr has N+1 entries indexing the GLOBAL arrays idx/eid
+ * (so idx[ptr[i]..ptr[i+1]) are the neighbours of node i); transpose=0 -> buckets by row
+ * (idx = message sources), transpose=1 -> buckets by col (idx = targets).  eid = original
+ * edge id.  *num_rel_edges = E_r. */
+int mpgnn_graph_relation_view(const mpgnn_graph* g, int64_t relation, int transpose, const int32_t** d_ptr,
+                              const int32_t** d_idx, const int32_t** d_eid, int64_t* num_rel_edges);
+/* Host copy of the number of edges of every relation (int64 [R]). */
+int mpgnn_graph_relation_counts(const mpgnn_graph* g, int64_t* h_counts);
+
+/* ---- K2: per-hop aggregation ----------------------------------------------------------
+ * PyG 2.3.1 MessagePassing.propagate(aggr='mean', flow='target_to_source') as called at
+ * mp_rgcn_layer.py:236: h[i,:] = sum_{e in E_r,row(e)=i} x[col(e),:] / max(1,deg_r(i)),
+ * fp32 sum in edge order.  transpose=1 gives the backward's un-normalised transpose
+ * gather  out[j,:] = init[j,:] + sum_{e in E_r,col(e)=j} x[row(e),:].  x/out row strides
+ * in floats; d_init may be NULL (zeros) or alias d_out. */
+int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, const float* d_x, int64_t ldx,
+               int64_t feat, const float* d_init, int64_t ldinit, float* d_out, int64_t ldout, void* stream);
+
+/* ---- K2+K3: one metapath hop, forward --------------------------------------------------
+ * CustomRGCNConv.forward(layer_num, relation, x, edge_index, edge_type)
+ * (mp_rgcn_layer.py:158-271) fused with the relu + dropout MPNetm applies to it
+ * (model.py:210-214):   y = drop(relu( mean_r(x) @ W + x @ root + bias )).
+ * d_h (N x f_in) receives the aggregated features kept for the backward.
+ * d_bias may be NULL.  dropout: p in [0,1); MPGNN_F_DROPOUT_MASK reads d_mask_bits
+ * ([N, ceil(f_out/8)] bytes, MSB first); MPGNN_F_DROPOUT_SEED draws from (seed, offset). */
+int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t f_in, const float* d_w,
+                  const float* d_root, const float* d_bias, int64_t f_out, uint32_t flags, float dropout_p,
+                  uint64_t seed, uint64_t offset, const uint8_t* d_mask_bits, float* d_h, float* d_y,
+                  void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- K4: one metapath hop, backward ----------------------------------------------------
+ * What autograd derives for the call above:
+ *   g_z = g_y * [y>0] (* 1/(1-p) under dropout);  g_bias = colsum g_z;
+ *   g_W = h^T g_z;  g_root = x^T g_z;  t = (g_z W^T)/deg;
+ *   g_x[j] = (g_z root^T)[j] + sum_{e in E_r, col(e)=j} t[row(e)]   (only with NEED_GX).
+ * Reductions over the N rows use a fixed split and a fixed summation order
+ * (deterministic, run-to-run and across GPU counts).  Gradients are WRITTEN, not
+ * accumulated.  d_gx may be NULL without MPGNN_F_NEED_GX. */
+int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, const float* d_h, const float* d_y,
+                  const float* d_gy, int64_t f_in, const float* d_w, const float* d_root, int64_t f_out,
+                  uint32_t flags, float dropout_p, float* d_gx, float* d_gw, float* d_groot, float* d_gbias,
+                  void* d_workspace, int64_t workspace_bytes, void* stream);
+/* Scratch both hop calls need for (N, f_in, f_out). */
+int64_t mpgnn_hop_workspace_bytes(int64_t num_nodes, int64_t f_in, int64_t f_out);
+
+/* ---- dense helpers used by the MPNetm head (model.py:220-226) and its backward ---------
+ * out[M,N] = epi( A[M,K] @ B + bias ), B(k,n) = d_b[k*ldb_k + n*ldb_n]; relu optional;
+ * d_gate (may be NULL): out *= [gate > 0] (ReLU backward).  A row stride lda, out ldo. */
+int mpgnn_gemm_rows(const float* d_a, int64_t lda, int64_t m, int64_t k, const float* d_b, int64_t ldb_k,
+                    int64_t ldb_n, int64_t n, const float* d_bias, int relu, const float* d_gate, int64_t ldgate,
+                    float* d_out, int64_t ldo, void* d_workspace, int64_t workspace_bytes, void* stream);
+/* out[K,N] = A[M,K]^T @ B[M,N] (reduction over the M rows, deterministic split);
+ * d_colsum (may be NULL) receives colsum(B) [N]. */
+int mpgnn_gemm_tn(const float* d_a, int64_t lda, int64_t m, int64_t k, const float* d_b, int64_t ldb, int64_t n,
+                  float* d_out, int64_t ldo, float* d_colsum, void* d_workspace, int64_t workspace_bytes,
+                  void* stream);
+int64_t mpgnn_gemm_workspace_bytes(int64_t m, int64_t k, int64_t n);
+
+/* ---- head: log_softmax + nll on an index set (main.py:1065, 1088, 1106) ----------------
+ * d_logits [N,C] -> d_logp [N,C]; *d_loss = -mean_i logp[idx[i], y[i]] (fixed-order sum);
+ * d_glogits (may be NULL) [N,C] = d loss / d logits (zero outside idx). */
+int mpgnn_logsoftmax_nll(const float* d_logits, int64_t num_nodes, int64_t num_classes, const int64_t* d_idx,
+                         const int64_t* d_y, int64_t n_idx, float* d_logp, float* d_loss, float* d_glogits,
+                         void* d_workspace, int64_t workspace_bytes, void* stream);
+/* K6: macro-F1 of argmax(logp[idx]) vs y, sklearn f1_score(average='macro') semantics
+ * (main.py:1090-1099, 1112): labels = union(pred, true); computed on device in double.
+ * d_confusion: int32 [C*C] scratch (zeroed by the call); d_f1: double [1]. */
+int mpgnn_macro_f1(const float* d_logp, int64_t num_classes, const int64_t* d_idx, const int64_t* d_y,
+                   int64_t n_idx, int32_t* d_confusion, double* d_f1, void* stream);
+
+/* ---- optimiser: torch.optim.Adam(lr, betas, eps, weight_decay) step (main.py:1119) ----
+ * One fused pass over n floats; `step` is the 1-based step count. */
+int mpgnn_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
+                    int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPGNN_B200_H */
