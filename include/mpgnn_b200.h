@@ -81,7 +81,7 @@ int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, 
  * d_bias may be NULL.  dropout: p in [0,1); MPGNN_F_DROPOUT_MASK reads d_mask_bits
  * ([N, ceil(f_out/8)] bytes, MSB first); MPGNN_F_DROPOUT_SEED draws from (seed, offset). */
 int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t f_in, const float* d_w,
-                  const float* d_root, const float* d_bias, int64_t f_out, uint32_t flags, float dropout_p,
+                  const float* d_root, const float* d_bias, int64_t f_out, uint32_t flags, double dropout_p,
                   uint64_t seed, uint64_t offset, const uint8_t* d_mask_bits, float* d_h, float* d_y,
                   void* d_workspace, int64_t workspace_bytes, void* stream);
 
@@ -95,7 +95,7 @@ int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int6
  * accumulated.  d_gx may be NULL without MPGNN_F_NEED_GX. */
 int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, const float* d_h, const float* d_y,
                   const float* d_gy, int64_t f_in, const float* d_w, const float* d_root, int64_t f_out,
-                  uint32_t flags, float dropout_p, float* d_gx, float* d_gw, float* d_groot, float* d_gbias,
+                  uint32_t flags, double dropout_p, float* d_gx, float* d_gw, float* d_groot, float* d_gbias,
                   void* d_workspace, int64_t workspace_bytes, void* stream);
 /* Scratch both hop calls need for (N, f_in, f_out). */
 int64_t mpgnn_hop_workspace_bytes(int64_t num_nodes, int64_t f_in, int64_t f_out);
@@ -128,7 +128,8 @@ int mpgnn_macro_f1(const float* d_logp, int64_t num_classes, const int64_t* d_id
 /* ---- optimiser: torch.optim.Adam(lr, betas, eps, weight_decay) step (main.py:1119) ----
  * One fused pass over n floats; `step` is the 1-based step count. */
 int mpgnn_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, int64_t n,
-                    int64_t step, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+                    int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                    void* stream);
 
 #ifdef __cplusplus
 }

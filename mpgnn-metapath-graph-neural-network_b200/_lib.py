@@ -1,0 +1,88 @@
+"""ctypes binding of libmpgnn_b200.so (the C ABI in include/mpgnn_b200.h).
+
+There is no CPU fallback: if the library is missing, or a call fails, this raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpgnn_b200.so")
+
+OK, EINVAL, ECUDA, ERANGE, ENOTSUP = 0, -1, -2, -3, -4
+F_RELU, F_DROPOUT_SEED, F_DROPOUT_MASK, F_NEED_GX, F_TF32X3, F_BF16 = 1, 2, 4, 8, 16, 32
+
+_c = ctypes
+_i64, _i32, _u32, _u64, _dbl, _ptr = _c.c_int64, _c.c_int, _c.c_uint32, _c.c_uint64, _c.c_double, _c.c_void_p
+
+# name -> (restype, argtypes); mirrors include/mpgnn_b200.h one to one
+PROTOTYPES = {
+    "mpgnn_last_error": (_c.c_char_p, []),
+    "mpgnn_abi_version": (_i32, []),
+    "mpgnn_graph_build": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _c.POINTER(_ptr)]),
+    "mpgnn_graph_build_host": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _c.POINTER(_ptr)]),
+    "mpgnn_graph_free": (None, [_ptr]),
+    "mpgnn_graph_info": (_i32, [_ptr, _c.POINTER(_i64), _c.POINTER(_i64), _c.POINTER(_i64)]),
+    "mpgnn_graph_relation_view": (_i32, [_ptr, _i64, _i32, _c.POINTER(_ptr), _c.POINTER(_ptr), _c.POINTER(_ptr),
+                                         _c.POINTER(_i64)]),
+    "mpgnn_graph_relation_counts": (_i32, [_ptr, _ptr]),
+    "mpgnn_spmm": (_i32, [_ptr, _i64, _i32, _i32, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr]),
+    "mpgnn_hop_fwd": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _u32, _dbl, _u64, _u64, _ptr, _ptr,
+                             _ptr, _ptr, _i64, _ptr]),
+    "mpgnn_hop_bwd": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _u32, _dbl, _ptr, _ptr,
+                             _ptr, _ptr, _ptr, _i64, _ptr]),
+    "mpgnn_hop_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "mpgnn_gemm_rows": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _ptr, _i32, _ptr, _i64, _ptr, _i64,
+                               _ptr, _i64, _ptr]),
+    "mpgnn_gemm_tn": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),
+    "mpgnn_gemm_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "mpgnn_logsoftmax_nll": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "mpgnn_macro_f1": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
+    "mpgnn_adam_step": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _ptr]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and type its entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "mpgnn_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().mpgnn_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc):
+    """Translate a status code into the exception the reference's Python path would raise."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc in (EINVAL, ERANGE):
+        raise ValueError("mpgnn_b200: " + msg)
+    if rc == ENOTSUP:
+        raise NotImplementedError("mpgnn_b200: " + msg)
+    raise RuntimeError("mpgnn_b200: " + msg)
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

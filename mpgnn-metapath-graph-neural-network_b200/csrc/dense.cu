@@ -1,0 +1,287 @@
+// Dense fp32 SIMT kernels: the exact-fp32 projection path (K3 baseline), the head GEMMs and
+// the deterministic weight-gradient reductions (K4).  Tall-skinny shapes: the node
+// dimension is huge, the feature dimensions are <= a few hundred.
+//
+// These are the general-shape kernels (any M/N/K, e.g. F_in=2 on layer 0, C=2 logits).
+// The tensor-core projection for the large aligned shapes lives in proj_tcgen05.cu.
+#include "common.cuh"
+
+namespace mpgnn {
+
+// ----------------------------------------------------------------------------------------
+// gemm_rows: out[M,N] = epi([A1|A2] @ B), B row-major [K,N]
+// ----------------------------------------------------------------------------------------
+constexpr int GR_BM = 128, GR_BN = 64, GR_BK = 16, GR_THREADS = 256, GR_PAD = 4;
+
+__global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
+  __shared__ __align__(16) float As[GR_BK][GR_BM + GR_PAD];
+  __shared__ __align__(16) float Bs[GR_BK][GR_BN];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int64_t row0 = (int64_t)blockIdx.x * GR_BM;
+  const int64_t col0 = (int64_t)blockIdx.y * GR_BN;
+  const int64_t ktot = a.k1 + a.k2;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int lk = tid % GR_BK, lm0 = tid / GR_BK;   // A loader: k fastest (coalesced along the row)
+  const int bn = tid % GR_BN, bk0 = tid / GR_BN;   // B loader
+  for (int64_t k0 = 0; k0 < ktot; k0 += GR_BK) {
+    const int64_t kk = k0 + lk;
+#pragma unroll
+    for (int p = 0; p < GR_BM / 16; ++p) {
+      const int m = lm0 + 16 * p;
+      const int64_t row = row0 + m;
+      float v = 0.f;
+      if (row < a.m) {
+        if (kk < a.k1) v = __ldg(a.a1 + row * a.lda1 + kk);
+        else if (kk < ktot) v = __ldg(a.a2 + row * a.lda2 + (kk - a.k1));
+      }
+      As[lk][m] = v;
+    }
+#pragma unroll
+    for (int p = 0; p < GR_BK / 4; ++p) {
+      const int k = bk0 + 4 * p;
+      const int64_t kg = k0 + k, ng = col0 + bn;
+      Bs[k][bn] = (kg < ktot && ng < a.n) ? __ldg(a.b + kg * a.n + ng) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GR_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const float scale = a.dropout_mode ? a.dropout_scale : 1.f;
+  const int64_t mask_ld = (a.n + 7) / 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = row0 + ty * 8 + i;
+    if (row >= a.m) continue;
+    float inv_deg_den = 1.f;
+    if (a.deg_ptr != nullptr) {
+      const int d = __ldg(a.deg_ptr + row + 1) - __ldg(a.deg_ptr + row);
+      inv_deg_den = (float)max(d, 1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t col = col0 + tx * 4 + j;
+      if (col >= a.n) continue;
+      float v = acc[i][j];
+      if (a.bias != nullptr) v += __ldg(a.bias + col);
+      if (col < a.deg_cols) v = v / inv_deg_den;
+      if (a.relu) v = fmaxf(v, 0.f);
+      if (a.gate != nullptr) v = (__ldg(a.gate + row * a.ldgate + col) > 0.f) ? v : 0.f;
+      if (a.dropout_mode == 1) {
+        v = dropout_keep(a.seed, a.offset, (uint64_t)row * (uint64_t)a.n + (uint64_t)col, a.dropout_p) ? v * scale : 0.f;
+      } else if (a.dropout_mode == 2) {
+        const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
+        v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;
+      }
+      a.out[row * a.ldo + col] = v;
+    }
+  }
+}
+
+int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s) {
+  if (a.m <= 0 || a.n <= 0) return MPGNN_OK;
+  MPGNN_REQUIRE(a.k1 >= 0 && a.k2 >= 0 && (a.k1 == 0 || a.a1) && (a.k2 == 0 || a.a2) && a.b && a.out, MPGNN_EINVAL,
+                "gemm_rows: bad arguments");
+  const int64_t gx = ceil_div(a.m, GR_BM), gy = ceil_div(a.n, GR_BN);
+  MPGNN_REQUIRE(gy <= 65535, MPGNN_ENOTSUP, "gemm_rows: N=%lld too wide", (long long)a.n);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  gemm_rows_kernel<<<grid, GR_THREADS, 0, s>>>(a);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// gemm_tn: out[K,N] = [A1|A2|1]^T @ B over the M rows; fixed split + fixed-order reduction
+// ----------------------------------------------------------------------------------------
+constexpr int TN_BK = 64, TN_BN = 64, TN_BR = 16, TN_THREADS = 256;
+
+static void tn_split(int64_t m, int64_t ktot, int64_t n, int64_t* splits, int64_t* rows_per_split) {
+  // a pure function of the shape => the same summation tree on every run and every GPU count
+  const int64_t tiles = ceil_div(ktot, TN_BK) * ceil_div(n, TN_BN);
+  int64_t target = (int64_t)kNumSMs * 8 / (tiles > 0 ? tiles : 1);
+  if (target < 1) target = 1;
+  int64_t sp = ceil_div(m, 512);
+  if (sp > target) sp = target;
+  if (sp < 1) sp = 1;
+  int64_t rps = align_up(ceil_div(m, sp), TN_BR);
+  sp = ceil_div(m, rps);
+  if (sp < 1) sp = 1;
+  *splits = sp;
+  *rows_per_split = rps;
+}
+
+int64_t gemm_tn_partial_floats(int64_t m, int64_t ktot, int64_t n) {
+  int64_t sp, rps;
+  tn_split(m, ktot, n, &sp, &rps);
+  return sp * ktot * n;
+}
+
+__global__ void __launch_bounds__(TN_THREADS) gemm_tn_kernel(GemmTnArgs a, int64_t ktot, int64_t rows_per_split,
+                                                              int tiles_n) {
+  __shared__ __align__(16) float As[TN_BR][TN_BK];
+  __shared__ __align__(16) float Bs[TN_BR][TN_BN];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int tile_k = blockIdx.x / tiles_n, tile_n = blockIdx.x % tiles_n;
+  const int64_t k0 = (int64_t)tile_k * TN_BK, n0 = (int64_t)tile_n * TN_BN;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(a.m, r_begin + rows_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lc = tid % 64, lr0 = tid / 64;
+  const int64_t kk = k0 + lc;
+  const int64_t nn = n0 + lc;
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += TN_BR) {
+#pragma unroll
+    for (int p = 0; p < TN_BR / 4; ++p) {
+      const int rr = lr0 + 4 * p;
+      const int64_t row = r0 + rr;
+      float av = 0.f, bv = 0.f;
+      if (row < r_end) {
+        if (kk < a.k1) av = __ldg(a.a1 + row * a.lda1 + kk);
+        else if (kk < a.k1 + a.k2) av = __ldg(a.a2 + row * a.lda2 + (kk - a.k1));
+        else if (kk < ktot) av = 1.f;  // the ones column: row ktot-1 of the output = colsum(B)
+        if (nn < a.n) bv = __ldg(a.b + row * a.ldb + nn);
+      }
+      As[rr][lc] = av;
+      Bs[rr][lc] = bv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < TN_BR; ++rr) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
+      const float aa[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* part = a.partials + (int64_t)blockIdx.y * ktot * a.n;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t kr = k0 + ty * 4 + i;
+    if (kr >= ktot) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t nc = n0 + tx * 4 + j;
+      if (nc < a.n) part[kr * a.n + nc] = acc[i][j];
+    }
+  }
+}
+
+__global__ void gemm_tn_reduce_kernel(GemmTnArgs a, int64_t ktot, int64_t splits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ktot * a.n) return;
+  float s = 0.f;
+  for (int64_t sp = 0; sp < splits; ++sp) s += a.partials[sp * ktot * a.n + i];  // fixed order
+  const int64_t kr = i / a.n, nc = i % a.n;
+  if (kr < a.k1) {
+    if (a.out1) a.out1[kr * a.ldo1 + nc] = s;
+  } else if (kr < a.k1 + a.k2) {
+    if (a.out2) a.out2[(kr - a.k1) * a.ldo2 + nc] = s;
+  } else if (a.out_ones) {
+    a.out_ones[nc] = s;
+  }
+}
+
+int launch_gemm_tn(const GemmTnArgs& a, cudaStream_t s) {
+  const int64_t ktot = a.k1 + a.k2 + (a.ones_row ? 1 : 0);
+  if (ktot <= 0 || a.n <= 0) return MPGNN_OK;
+  MPGNN_REQUIRE(a.m >= 0 && a.b && a.partials, MPGNN_EINVAL, "gemm_tn: bad arguments");
+  int64_t splits, rps;
+  tn_split(a.m > 0 ? a.m : 1, ktot, a.n, &splits, &rps);
+  MPGNN_REQUIRE(splits * ktot * a.n <= a.partial_capacity_floats, MPGNN_EINVAL, "gemm_tn: workspace too small");
+  MPGNN_REQUIRE(splits <= 65535, MPGNN_ENOTSUP, "gemm_tn: too many splits");
+  const int tiles_n = (int)ceil_div(a.n, TN_BN);
+  const int64_t tiles = ceil_div(ktot, TN_BK) * tiles_n;
+  dim3 grid((unsigned)tiles, (unsigned)splits);
+  gemm_tn_kernel<<<grid, TN_THREADS, 0, s>>>(a, ktot, rps, tiles_n);
+  MPGNN_LAUNCH_CHECK();
+  const int64_t total = ktot * a.n;
+  gemm_tn_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a, ktot, splits);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------
+__global__ void pack_b_kernel(float* dst, int64_t ldd, const float* __restrict__ src, int64_t sk, int64_t sn,
+                              int64_t k, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * n) return;
+  const int64_t kk = i / n, nn = i % n;
+  dst[kk * ldd + nn] = src[kk * sk + nn * sn];
+}
+
+int launch_pack_b(float* dst, int64_t ldd, const float* src, int64_t src_ld_k, int64_t src_ld_n, int64_t k,
+                  int64_t n, cudaStream_t s) {
+  if (k <= 0 || n <= 0) return MPGNN_OK;
+  pack_b_kernel<<<(unsigned)ceil_div(k * n, 256), 256, 0, s>>>(dst, ldd, src, src_ld_k, src_ld_n, k, n);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+__global__ void relu_dropout_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, float scale,
+                                        float* __restrict__ gz, int64_t count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    gz[i] = (y[i] > 0.f) ? gy[i] * scale : 0.f;
+}
+
+__global__ void relu_dropout_bwd_kernel_v4(const float4* __restrict__ gy, const float4* __restrict__ y, float scale,
+                                           float4* __restrict__ gz, int64_t count4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += stride) {
+    const float4 g = gy[i], v = y[i];
+    float4 o;
+    o.x = v.x > 0.f ? g.x * scale : 0.f;
+    o.y = v.y > 0.f ? g.y * scale : 0.f;
+    o.z = v.z > 0.f ? g.z * scale : 0.f;
+    o.w = v.w > 0.f ? g.w * scale : 0.f;
+    gz[i] = o;
+  }
+}
+
+int launch_relu_dropout_bwd(const float* gy, const float* y, float scale, float* gz, int64_t count, cudaStream_t s) {
+  if (count <= 0) return MPGNN_OK;
+  const bool v4 = count % 4 == 0 && ((uintptr_t)gy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)gz % 16 == 0);
+  const int64_t work = v4 ? count / 4 : count;
+  int64_t blocks = ceil_div(work, 256);
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  if (v4)
+    relu_dropout_bwd_kernel_v4<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(gy),
+                                                               reinterpret_cast<const float4*>(y), scale,
+                                                               reinterpret_cast<float4*>(gz), work);
+  else
+    relu_dropout_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(gy, y, scale, gz, count);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+}  // namespace mpgnn

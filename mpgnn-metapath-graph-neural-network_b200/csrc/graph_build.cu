@@ -1,0 +1,370 @@
+// K1 -- relation-typed CSR / CSC construction.
+//
+// Replaces the reference's per-call `masked_edge_index(edge_index, edge_type == relation)`
+// (mp_rgcn_layer.py:29-37, :231): the whole edge list is bucketed ONCE by
+// key = relation*N + node with a stable LSD radix sort (8-bit digits, per-block digit
+// histograms, one global exclusive scan, stable in-block ranking), so bucket (r,i) lists
+// its edges in original edge order, duplicates kept.  Integer work, HBM bound, bit exact.
+#include "common.cuh"
+
+namespace mpgnn {
+
+// ----------------------------------------------------------------------------------------
+// device-wide exclusive scan (reduce -> scan of block sums -> downsweep; no inter-block waits)
+// ----------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t ws = lane < (SCAN_THREADS / 32) ? warp_sums[lane] : 0u;
+    uint32_t winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (SCAN_THREADS / 32)) warp_sums[lane] = winc - ws;  // exclusive warp offsets
+    if (lane == (SCAN_THREADS / 32) - 1) warp_sums[SCAN_THREADS / 32] = winc;
+  }
+  __syncthreads();
+  *total = warp_sums[SCAN_THREADS / 32];
+  return warp_sums[w] + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, int64_t n,
+                                                                    uint32_t* __restrict__ block_sums) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32 + 1];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t p = base + (int64_t)i * SCAN_THREADS + threadIdx.x;
+    if (p < n) s += in[p];
+  }
+  uint32_t total;
+  block_exclusive_scan(s, &total, warp_sums);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_downsweep_kernel(const uint32_t* __restrict__ in,
+                                                                       uint32_t* __restrict__ out, int64_t n,
+                                                                       const uint32_t* __restrict__ block_offsets) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32 + 1];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = (base + i < n) ? in[base + i] : 0u;
+    s += v[i];
+  }
+  uint32_t total;
+  uint32_t run = block_exclusive_scan(s, &total, warp_sums) + (block_offsets ? block_offsets[blockIdx.x] : 0u);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) out[base + i] = run;
+    run += v[i];
+  }
+}
+
+int64_t exclusive_scan_tmp_bytes(int64_t n) {
+  int64_t bytes = 0;
+  while (n > 1) {
+    n = ceil_div(n, SCAN_TILE);
+    bytes += align_up(n * 4, 256);
+  }
+  return bytes + 256;
+}
+
+int exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, int64_t n, void* d_tmp, int64_t tmp_bytes,
+                       cudaStream_t s) {
+  if (n <= 0) return MPGNN_OK;
+  MPGNN_REQUIRE(tmp_bytes >= exclusive_scan_tmp_bytes(n), MPGNN_EINVAL, "exclusive_scan: workspace too small");
+  const int64_t nb = ceil_div(n, SCAN_TILE);
+  if (nb == 1) {
+    scan_downsweep_kernel<<<1, SCAN_THREADS, 0, s>>>(d_in, d_out, n, nullptr);
+    MPGNN_LAUNCH_CHECK();
+    return MPGNN_OK;
+  }
+  uint32_t* sums = static_cast<uint32_t*>(d_tmp);
+  scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(d_in, n, sums);
+  MPGNN_LAUNCH_CHECK();
+  char* next = static_cast<char*>(d_tmp) + align_up(nb * 4, 256);
+  MPGNN_PROPAGATE(exclusive_scan_u32(sums, sums, nb, next, tmp_bytes - align_up(nb * 4, 256), s));
+  scan_downsweep_kernel<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(d_in, d_out, n, sums);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// keys
+// ----------------------------------------------------------------------------------------
+__global__ void make_keys_kernel(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_type,
+                                 int64_t e, int64_t n, int64_t r, int which, uint32_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals, int* __restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= e) return;
+  int64_t rel = edge_type[i];
+  int64_t row = edge_index[i];
+  int64_t col = edge_index[e + i];
+  if (rel < 0 || rel >= r || row < 0 || row >= n || col < 0 || col >= n) {
+    *err = 1;
+    rel = 0;
+    row = 0;
+    col = 0;
+  }
+  keys[i] = (uint32_t)(rel * n + (which == 0 ? row : col));
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void count_keys_kernel(const uint32_t* __restrict__ keys, int64_t e, uint32_t* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < e) atomicAdd(&counts[keys[i]], 1u);  // integer counts: order independent
+}
+
+__global__ void gather_other_kernel(const int64_t* __restrict__ edge_index, int64_t e, int which,
+                                    const uint32_t* __restrict__ eid, int32_t* __restrict__ idx,
+                                    int32_t* __restrict__ eid_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= e) return;
+  uint32_t src = eid[i];
+  // CSR (which=0) stores the message source = edge_index[1]; CSC stores the target = edge_index[0]
+  idx[i] = (int32_t)edge_index[(which == 0 ? e : 0) + (int64_t)src];
+  eid_out[i] = (int32_t)src;
+}
+
+// ----------------------------------------------------------------------------------------
+// stable LSD radix sort pass (8-bit digit)
+// ----------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_WARP_SPAN = 32 * RS_ITEMS;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n,
+                                                                 int shift, uint32_t* __restrict__ hist,
+                                                                 int64_t nb) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    int64_t p = base + (int64_t)i * RS_THREADS + threadIdx.x;
+    if (p < n) atomicAdd(&h[(keys[p] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];  // digit-major for the global scan
+}
+
+// Order of the keys inside a tile: warp-major, then iteration, then lane.  The rank of a
+// key among equal digits follows exactly that order, which keeps the pass stable.
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, int64_t n, int shift, const uint32_t* __restrict__ offs, int64_t nb) {
+  __shared__ uint32_t cnt[RS_WARPS][256];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * RS_WARP_SPAN;
+  uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const int64_t p = wbase + it * 32 + lane;
+    const bool valid = p < n;
+    key[it] = valid ? keys_in[p] : 0u;
+    val[it] = valid ? vals_in[p] : 0u;
+    rank[it] = 0;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const uint32_t d = (key[it] >> shift) & 255u;
+      const unsigned peers = __match_any_sync(act, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) {
+        old = cnt[w][d];
+        cnt[w][d] = old + __popc(peers);
+      }
+      old = __shfl_sync(peers, old, leader);
+      rank[it] = old + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;  // one thread per digit: warp-exclusive offsets + global base
+    uint32_t run = offs[(int64_t)d * nb + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ++ww) {
+      uint32_t c = cnt[ww][d];
+      cnt[ww][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < RS_ITEMS; ++it) {
+    const int64_t p = wbase + it * 32 + lane;
+    if (p < n) {
+      const uint32_t d = (key[it] >> shift) & 255u;
+      const uint32_t pos = cnt[w][d] + rank[it];
+      keys_out[pos] = key[it];
+      vals_out[pos] = val[it];
+    }
+  }
+}
+
+static int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int64_t n,
+                            int key_bits, uint32_t* hist, void* scan_tmp, int64_t scan_tmp_bytes, cudaStream_t s,
+                            uint32_t** keys_sorted, uint32_t** vals_sorted) {
+  const int64_t nb = ceil_div(n, RS_TILE);
+  uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
+  for (int shift = 0; shift < key_bits; shift += 8) {
+    radix_hist_kernel<<<(unsigned)nb, RS_THREADS, 0, s>>>(ki, n, shift, hist, nb);
+    MPGNN_LAUNCH_CHECK();
+    MPGNN_PROPAGATE(exclusive_scan_u32(hist, hist, 256 * nb, scan_tmp, scan_tmp_bytes, s));
+    radix_scatter_kernel<<<(unsigned)nb, RS_THREADS, 0, s>>>(ki, vi, ko, vo, n, shift, hist, nb);
+    MPGNN_LAUNCH_CHECK();
+    uint32_t* t;
+    t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+  }
+  *keys_sorted = ki;
+  *vals_sorted = vi;
+  return MPGNN_OK;
+}
+
+static void free_graph(mpgnn_graph_impl* g) {
+  if (!g) return;
+  cudaFree(g->csr_ptr);
+  cudaFree(g->csr_idx);
+  cudaFree(g->csr_eid);
+  cudaFree(g->csc_ptr);
+  cudaFree(g->csc_idx);
+  cudaFree(g->csc_eid);
+  free(g->rel_offsets_host);
+  delete g;
+}
+
+int graph_build_device(const int64_t* d_edge_index, const int64_t* d_edge_type, int64_t e, int64_t n, int64_t r,
+                       cudaStream_t s, mpgnn_graph_impl** out) {
+  MPGNN_REQUIRE(out != nullptr, MPGNN_EINVAL, "graph_build: out is NULL");
+  MPGNN_REQUIRE(n >= 1 && r >= 1 && e >= 0, MPGNN_EINVAL, "graph_build: need N>=1, R>=1, E>=0 (N=%lld R=%lld E=%lld)",
+                (long long)n, (long long)r, (long long)e);
+  MPGNN_REQUIRE(e < (1LL << 31), MPGNN_ENOTSUP, "graph_build: E=%lld does not fit int32 positions", (long long)e);
+  MPGNN_REQUIRE(n < (1LL << 31) && r * n < (1LL << 32) - 1, MPGNN_ENOTSUP,
+                "graph_build: R*N=%lld does not fit the 32-bit (relation,node) key", (long long)(r * n));
+  MPGNN_REQUIRE(e == 0 || (d_edge_index && d_edge_type), MPGNN_EINVAL, "graph_build: NULL edge arrays");
+  const int64_t nk = r * n + 1;
+  int key_bits = 1;
+  while ((1LL << key_bits) < r * n) ++key_bits;
+
+  mpgnn_graph_impl* g = new mpgnn_graph_impl();
+  memset(g, 0, sizeof(*g));
+  g->n = n; g->e = e; g->r = r;
+  const int64_t e1 = e > 0 ? e : 1;
+  cudaError_t ce = cudaSuccess;
+  if (ce == cudaSuccess) ce = cudaMalloc(&g->csr_ptr, nk * 4);
+  if (ce == cudaSuccess) ce = cudaMalloc(&g->csc_ptr, nk * 4);
+  if (ce == cudaSuccess) ce = cudaMalloc(&g->csr_idx, e1 * 4);
+  if (ce == cudaSuccess) ce = cudaMalloc(&g->csr_eid, e1 * 4);
+  if (ce == cudaSuccess) ce = cudaMalloc(&g->csc_idx, e1 * 4);
+  if (ce == cudaSuccess) ce = cudaMalloc(&g->csc_eid, e1 * 4);
+  g->rel_offsets_host = static_cast<int64_t*>(calloc(r + 1, sizeof(int64_t)));
+  if (ce != cudaSuccess || !g->rel_offsets_host) {
+    set_error("graph_build: allocation failed (%s)", cudaGetErrorString(ce));
+    free_graph(g);
+    return MPGNN_ECUDA;
+  }
+
+  // temporaries (stream ordered)
+  const int64_t nb = ceil_div(e1, RS_TILE);
+  const int64_t scan_n = (256 * nb > nk) ? 256 * nb : nk;
+  const int64_t scan_bytes = exclusive_scan_tmp_bytes(scan_n);
+  uint32_t *keys_a = nullptr, *vals_a = nullptr, *keys_b = nullptr, *vals_b = nullptr, *hist = nullptr;
+  void* scan_tmp = nullptr;
+  int* d_err = nullptr;
+  int32_t* h_ptr_samples = nullptr;
+  int rc = MPGNN_OK;
+#define BUILD_CHECK(expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess && rc == MPGNN_OK) {                                                    \
+      set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));            \
+      rc = MPGNN_ECUDA;                                                                           \
+    }                                                                                             \
+  } while (0)
+  BUILD_CHECK(cudaMalloc(&keys_a, e1 * 4));
+  BUILD_CHECK(cudaMalloc(&vals_a, e1 * 4));
+  BUILD_CHECK(cudaMalloc(&keys_b, e1 * 4));
+  BUILD_CHECK(cudaMalloc(&vals_b, e1 * 4));
+  BUILD_CHECK(cudaMalloc(&hist, 256 * nb * 4));
+  BUILD_CHECK(cudaMalloc(&scan_tmp, scan_bytes));
+  BUILD_CHECK(cudaMalloc(&d_err, sizeof(int)));
+  h_ptr_samples = static_cast<int32_t*>(malloc((r + 1) * sizeof(int32_t)));
+  if (rc == MPGNN_OK) BUILD_CHECK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+
+  for (int which = 0; which < 2 && rc == MPGNN_OK; ++which) {
+    int32_t* ptr = which == 0 ? g->csr_ptr : g->csc_ptr;
+    int32_t* idx = which == 0 ? g->csr_idx : g->csc_idx;
+    int32_t* eid = which == 0 ? g->csr_eid : g->csc_eid;
+    BUILD_CHECK(cudaMemsetAsync(ptr, 0, nk * 4, s));
+    if (e > 0 && rc == MPGNN_OK) {
+      const unsigned eb = (unsigned)ceil_div(e, 256);
+      make_keys_kernel<<<eb, 256, 0, s>>>(d_edge_index, d_edge_type, e, n, r, which, keys_a, vals_a, d_err);
+      BUILD_CHECK(cudaGetLastError());
+      count_keys_kernel<<<eb, 256, 0, s>>>(keys_a, e, reinterpret_cast<uint32_t*>(ptr));
+      BUILD_CHECK(cudaGetLastError());
+      uint32_t *ks = nullptr, *vs = nullptr;
+      if (rc == MPGNN_OK)
+        rc = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, e, key_bits, hist, scan_tmp, scan_bytes, s, &ks, &vs);
+      if (rc == MPGNN_OK) {
+        gather_other_kernel<<<eb, 256, 0, s>>>(d_edge_index, e, which, vs, idx, eid);
+        BUILD_CHECK(cudaGetLastError());
+      }
+    }
+    if (rc == MPGNN_OK)
+      rc = exclusive_scan_u32(reinterpret_cast<uint32_t*>(ptr), reinterpret_cast<uint32_t*>(ptr), nk, scan_tmp,
+                              scan_bytes, s);
+  }
+  int h_err = 0;
+  if (rc == MPGNN_OK) {
+    BUILD_CHECK(cudaMemcpy2DAsync(h_ptr_samples, 4, g->csr_ptr, (size_t)n * 4, 4, (size_t)(r + 1),
+                                  cudaMemcpyDeviceToHost, s));
+    BUILD_CHECK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  BUILD_CHECK(cudaStreamSynchronize(s));
+#undef BUILD_CHECK
+  cudaFree(keys_a); cudaFree(vals_a); cudaFree(keys_b); cudaFree(vals_b);
+  cudaFree(hist); cudaFree(scan_tmp); cudaFree(d_err);
+  if (rc == MPGNN_OK && h_err) {
+    set_error("graph_build: an edge names a node outside [0,%lld) or a relation outside [0,%lld)", (long long)n,
+              (long long)r);
+    rc = MPGNN_ERANGE;
+  }
+  if (rc == MPGNN_OK)
+    for (int64_t k = 0; k <= r; ++k) g->rel_offsets_host[k] = h_ptr_samples[k];
+  free(h_ptr_samples);
+  if (rc != MPGNN_OK) {
+    free_graph(g);
+    return rc;
+  }
+  *out = g;
+  return MPGNN_OK;
+}
+
+void graph_free(mpgnn_graph_impl* g) { free_graph(g); }
+
+}  // namespace mpgnn

@@ -1,0 +1,111 @@
+// One metapath hop = CustomRGCNConv.forward (mp_rgcn_layer.py:158-271) + the relu/dropout
+// MPNetm applies to it (model.py:210-214), and the matching backward.
+// Orchestrates K2 (spmm.cu), K3/K4 dense kernels (dense.cu / proj_tcgen05.cu).
+#include "common.cuh"
+
+namespace mpgnn {
+
+int proj_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags);
+int launch_proj_tcgen05(const GemmRowsArgs& a, uint32_t flags, cudaStream_t s);
+
+static int64_t fwd_ws_floats(int64_t f_in, int64_t f_out) { return align_up(2 * f_in * f_out, 64); }
+
+int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
+  int64_t floats = 0;
+  floats += fwd_ws_floats(f_in, f_out);                                // packed [W;root]
+  floats += align_up(n * f_out, 64);                                   // g_z
+  floats += align_up(gemm_tn_partial_floats(n, 2 * f_in + 1, f_out), 64);  // split-K partials
+  floats += align_up(f_out * 2 * f_in, 64);                            // packed [W^T | root^T]
+  floats += align_up(n * 2 * f_in, 64);                                // [t | g_z root^T]
+  return floats * 4 + 8 * 256;
+}
+
+int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
+            const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
+            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s) {
+  MPGNN_REQUIRE(g && x && w && root && h && y, MPGNN_EINVAL, "hop_fwd: NULL argument");
+  MPGNN_REQUIRE(rel >= 0 && rel < g->r, MPGNN_ERANGE, "hop_fwd: relation %lld outside [0,%lld)", (long long)rel,
+                (long long)g->r);
+  MPGNN_REQUIRE(f_in >= 1 && f_out >= 1, MPGNN_EINVAL, "hop_fwd: bad feature sizes");
+  const bool drop_seed = flags & MPGNN_F_DROPOUT_SEED, drop_mask = flags & MPGNN_F_DROPOUT_MASK;
+  MPGNN_REQUIRE(!(drop_seed && drop_mask), MPGNN_EINVAL, "hop_fwd: both dropout modes set");
+  MPGNN_REQUIRE(!(drop_seed || drop_mask) || (p >= 0.0 && p < 1.0), MPGNN_EINVAL, "hop_fwd: dropout p=%g", p);
+  MPGNN_REQUIRE(!drop_mask || mask_bits, MPGNN_EINVAL, "hop_fwd: mask mode without mask");
+  Workspace ws(ws_ptr, ws_bytes);
+  float* bp = ws.take<float>(fwd_ws_floats(f_in, f_out));
+  MPGNN_REQUIRE(bp != nullptr, MPGNN_EINVAL, "hop_fwd: workspace too small");
+
+  const int32_t* ptr = g->csr_ptr + rel * g->n;
+  MPGNN_PROPAGATE(launch_spmm(ptr, g->csr_idx, g->n, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp, w, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp + f_in * f_out, root, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
+
+  GemmRowsArgs a{};
+  a.a1 = h; a.lda1 = f_in; a.k1 = f_in;
+  a.a2 = x; a.lda2 = f_in; a.k2 = f_in;
+  a.b = bp; a.m = g->n; a.n = f_out;
+  a.bias = bias;
+  a.relu = (flags & MPGNN_F_RELU) ? 1 : 0;
+  a.dropout_mode = drop_seed ? 1 : (drop_mask ? 2 : 0);
+  a.dropout_p = (float)p; a.dropout_scale = (float)(1.0 / (1.0 - p)); a.seed = seed; a.offset = offset; a.mask_bits = mask_bits;
+  a.out = y; a.ldo = f_out;
+  if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags))
+    return launch_proj_tcgen05(a, flags, s);
+  return launch_gemm_rows(a, s);
+}
+
+int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y, const float* gy,
+            int64_t f_in, const float* w, const float* root, int64_t f_out, uint32_t flags, double p, float* gx,
+            float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes, cudaStream_t s) {
+  MPGNN_REQUIRE(g && x && h && y && gy && w && root && gw && groot, MPGNN_EINVAL, "hop_bwd: NULL argument");
+  MPGNN_REQUIRE(rel >= 0 && rel < g->r, MPGNN_ERANGE, "hop_bwd: relation %lld outside [0,%lld)", (long long)rel,
+                (long long)g->r);
+  const bool need_gx = flags & MPGNN_F_NEED_GX;
+  MPGNN_REQUIRE(!need_gx || gx, MPGNN_EINVAL, "hop_bwd: NEED_GX without d_gx");
+  const bool drop = flags & (MPGNN_F_DROPOUT_SEED | MPGNN_F_DROPOUT_MASK);
+  const int64_t n = g->n;
+  Workspace ws(ws_ptr, ws_bytes);
+  (void)ws.take<float>(fwd_ws_floats(f_in, f_out));
+  float* gz = ws.take<float>(align_up(n * f_out, 64));
+  const int64_t part_floats = gemm_tn_partial_floats(n, 2 * f_in + 1, f_out);
+  float* partials = ws.take<float>(align_up(part_floats, 64));
+  float* bp2 = ws.take<float>(align_up(f_out * 2 * f_in, 64));
+  float* t = need_gx ? ws.take<float>(align_up(n * 2 * f_in, 64)) : nullptr;
+  MPGNN_REQUIRE(gz && partials && bp2 && (!need_gx || t), MPGNN_EINVAL, "hop_bwd: workspace too small");
+
+  const float* gz_src = gy;
+  if (flags & MPGNN_F_RELU) {
+    const float scale = drop ? (float)(1.0 / (1.0 - p)) : 1.f;
+    MPGNN_PROPAGATE(launch_relu_dropout_bwd(gy, y, scale, gz, n * f_out, s));
+    gz_src = gz;
+  }
+  GemmTnArgs tn{};
+  tn.a1 = h; tn.lda1 = f_in; tn.k1 = f_in;
+  tn.a2 = x; tn.lda2 = f_in; tn.k2 = f_in;
+  tn.ones_row = 1;
+  tn.b = gz_src; tn.ldb = f_out; tn.n = f_out; tn.m = n;
+  tn.out1 = gw; tn.ldo1 = f_out;
+  tn.out2 = groot; tn.ldo2 = f_out;
+  tn.out_ones = gbias;
+  tn.partials = partials; tn.partial_capacity_floats = part_floats;
+  MPGNN_PROPAGATE(launch_gemm_tn(tn, s));
+
+  if (need_gx) {
+    // [t | g_z root^T] = g_z @ [W^T | root^T], first f_in columns divided by deg_r(row)
+    MPGNN_PROPAGATE(launch_pack_b(bp2, 2 * f_in, w, 1, f_out, f_out, f_in, s));
+    MPGNN_PROPAGATE(launch_pack_b(bp2 + f_in, 2 * f_in, root, 1, f_out, f_out, f_in, s));
+    GemmRowsArgs a{};
+    a.a1 = gz_src; a.lda1 = f_out; a.k1 = f_out;
+    a.a2 = nullptr; a.lda2 = 0; a.k2 = 0;
+    a.b = bp2; a.m = n; a.n = 2 * f_in;
+    a.deg_ptr = g->csr_ptr + rel * n; a.deg_cols = f_in;
+    a.out = t; a.ldo = 2 * f_in;
+    MPGNN_PROPAGATE(launch_gemm_rows(a, s));
+    // g_x[j] = (g_z root^T)[j] + sum_{e: col(e)=j} t[row(e)]
+    MPGNN_PROPAGATE(launch_spmm(g->csc_ptr + rel * n, g->csc_idx, n, /*mean=*/0, t, 2 * f_in, f_in, t + f_in,
+                                2 * f_in, gx, f_in, s));
+  }
+  return MPGNN_OK;
+}
+
+}  // namespace mpgnn

@@ -1,0 +1,171 @@
+// K2 -- per-hop aggregation along one relation (CSR gather, optional mean).
+//
+// Restates PyG 2.3.1 propagate(aggr='mean', flow='target_to_source') as the reference calls
+// it (mp_rgcn_layer.py:236): out[i,:] = sum_{p in bucket(r,i)} x[idx[p],:] / max(1,deg).
+// The per-row sum runs in bucket order = original edge order, i.e. the order the
+// reference's CPU scatter_add_ uses, starting from 0 like its zero-initialised buffer.
+//
+// HBM bound.  A group of LPR lanes owns one output row and covers its features with
+// VEC-wide (128-bit for VEC=4) loads; a warp therefore streams 32/LPR consecutive rows per
+// iteration (512 B per row at F=128).  Neighbour indices of a row are fetched with one
+// coalesced load per 32-edge batch and broadcast with shuffles, so high-degree rows cost
+// one index transaction per 32 gathers; gathers are issued 4 deep before the dependent adds.
+// Grid = a multiple of the SM count, each warp walks row-groups with a grid stride.
+#include "common.cuh"
+
+namespace mpgnn {
+
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> { using type = float4; };
+template <>
+struct VecT<2> { using type = float2; };
+template <>
+struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ void vadd(typename VecT<VEC>::type& a, const typename VecT<VEC>::type& b);
+template <>
+__device__ __forceinline__ void vadd<4>(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+template <>
+__device__ __forceinline__ void vadd<2>(float2& a, const float2& b) { a.x += b.x; a.y += b.y; }
+template <>
+__device__ __forceinline__ void vadd<1>(float& a, const float& b) { a += b; }
+
+template <int VEC>
+__device__ __forceinline__ void vdiv(typename VecT<VEC>::type& a, float d);
+template <>
+__device__ __forceinline__ void vdiv<4>(float4& a, float d) { a.x /= d; a.y /= d; a.z /= d; a.w /= d; }
+template <>
+__device__ __forceinline__ void vdiv<2>(float2& a, float d) { a.x /= d; a.y /= d; }
+template <>
+__device__ __forceinline__ void vdiv<1>(float& a, float d) { a /= d; }
+
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::type vzero();
+template <>
+__device__ __forceinline__ float4 vzero<4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <>
+__device__ __forceinline__ float2 vzero<2>() { return make_float2(0.f, 0.f); }
+template <>
+__device__ __forceinline__ float vzero<1>() { return 0.f; }
+
+// units = feat / VEC vector slots per row; lane u of the group covers slots u, u+LPR, ...
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(256) spmm_gather_kernel(const int32_t* __restrict__ ptr,
+                                                          const int32_t* __restrict__ idx, int64_t n_rows,
+                                                          int mean, const float* __restrict__ x, int64_t ldx,
+                                                          int units, const float* __restrict__ init,
+                                                          int64_t ldinit, float* __restrict__ out, int64_t ldout) {
+  using V = typename VecT<VEC>::type;
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;          // lane inside the row group
+  const int grp = lane / LPR;          // which of the warp's rows
+  const unsigned grp_mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_groups = (n_rows + ROWS_PER_WARP - 1) / ROWS_PER_WARP;
+
+  for (int64_t gi = warp_id; gi < n_groups; gi += n_warps) {
+    const int64_t row = gi * ROWS_PER_WARP + grp;
+    const bool row_ok = row < n_rows;
+    int32_t beg = 0, end = 0;
+    if (row_ok) {
+      beg = __ldg(ptr + row);
+      end = __ldg(ptr + row + 1);
+    }
+    const int deg = end - beg;
+    for (int u0 = 0; u0 < units; u0 += LPR) {   // feature chunks (one pass when feat <= 32*VEC)
+      const int u = u0 + sub;
+      const bool u_ok = row_ok && u < units;
+      V acc = vzero<VEC>();
+      if (init != nullptr && u_ok) acc = *reinterpret_cast<const V*>(init + row * ldinit + (int64_t)u * VEC);
+      for (int32_t b = beg; b < end; b += LPR) {
+        // one coalesced index load per LPR edges, broadcast inside the row group
+        const int32_t my = (b + sub < end) ? __ldg(idx + b + sub) : 0;
+        const int cnt = min(LPR, end - b);
+        int k = 0;
+        for (; k + 4 <= cnt; k += 4) {
+          const int32_t c0 = __shfl_sync(grp_mask, my, grp * LPR + k + 0);
+          const int32_t c1 = __shfl_sync(grp_mask, my, grp * LPR + k + 1);
+          const int32_t c2 = __shfl_sync(grp_mask, my, grp * LPR + k + 2);
+          const int32_t c3 = __shfl_sync(grp_mask, my, grp * LPR + k + 3);
+          if (u_ok) {
+            const V v0 = __ldg(reinterpret_cast<const V*>(x + (int64_t)c0 * ldx + (int64_t)u * VEC));
+            const V v1 = __ldg(reinterpret_cast<const V*>(x + (int64_t)c1 * ldx + (int64_t)u * VEC));
+            const V v2 = __ldg(reinterpret_cast<const V*>(x + (int64_t)c2 * ldx + (int64_t)u * VEC));
+            const V v3 = __ldg(reinterpret_cast<const V*>(x + (int64_t)c3 * ldx + (int64_t)u * VEC));
+            vadd<VEC>(acc, v0);
+            vadd<VEC>(acc, v1);
+            vadd<VEC>(acc, v2);
+            vadd<VEC>(acc, v3);
+          }
+        }
+        for (; k < cnt; ++k) {
+          const int32_t c = __shfl_sync(grp_mask, my, grp * LPR + k);
+          if (u_ok) {
+            const V v = __ldg(reinterpret_cast<const V*>(x + (int64_t)c * ldx + (int64_t)u * VEC));
+            vadd<VEC>(acc, v);
+          }
+        }
+      }
+      if (u_ok) {
+        if (mean && deg > 1) vdiv<VEC>(acc, (float)deg);
+        *reinterpret_cast<V*>(out + row * ldout + (int64_t)u * VEC) = acc;
+      }
+    }
+  }
+}
+
+template <int VEC, int LPR>
+static int launch_one(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
+                      int units, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
+  constexpr int ROWS_PER_WARP = 32 / LPR;
+  const int64_t n_groups = ceil_div(n_rows, ROWS_PER_WARP);
+  const int64_t blocks_needed = ceil_div(n_groups, 8);  // 8 warps per block
+  // several row-groups per warp once the graph is large; grid a multiple of the SM count
+  int64_t blocks = blocks_needed;
+  const int64_t cap = (int64_t)kNumSMs * 8 * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks > kNumSMs) blocks = (blocks / kNumSMs) * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  spmm_gather_kernel<VEC, LPR><<<(unsigned)blocks, 256, 0, s>>>(ptr, idx, n_rows, mean, x, ldx, units, init, ldinit,
+                                                             out, ldout);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+template <int VEC>
+static int launch_vec(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
+                      int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
+  const int units = (int)(feat / VEC);
+#define MPGNN_SPMM_CASE(L) \
+  return launch_one<VEC, L>(ptr, idx, n_rows, mean, x, ldx, units, init, ldinit, out, ldout, s)
+  if (units <= 1) MPGNN_SPMM_CASE(1);
+  if (units <= 2) MPGNN_SPMM_CASE(2);
+  if (units <= 4) MPGNN_SPMM_CASE(4);
+  if (units <= 8) MPGNN_SPMM_CASE(8);
+  if (units <= 16) MPGNN_SPMM_CASE(16);
+  MPGNN_SPMM_CASE(32);
+#undef MPGNN_SPMM_CASE
+}
+
+static bool aligned_to(const void* p, int64_t bytes) { return (reinterpret_cast<uintptr_t>(p) % bytes) == 0; }
+
+int launch_spmm(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
+                int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
+  if (n_rows <= 0 || feat <= 0) return MPGNN_OK;
+  MPGNN_REQUIRE(feat <= (1 << 20), MPGNN_ENOTSUP, "spmm: feature width %lld too large", (long long)feat);
+  const bool has_init = init != nullptr;
+  auto ok = [&](int64_t v) {
+    return feat % v == 0 && ldx % v == 0 && ldout % v == 0 && (!has_init || ldinit % v == 0) &&
+           aligned_to(x, v * 4) && aligned_to(out, v * 4) && (!has_init || aligned_to(init, v * 4));
+  };
+  if (ok(4)) return launch_vec<4>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, s);
+  if (ok(2)) return launch_vec<2>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, s);
+  return launch_vec<1>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, s);
+}
+
+}  // namespace mpgnn

@@ -1,0 +1,120 @@
+"""Device-resident relation-typed CSR/CSC (K1) and the cache that lets the reference's
+call shape -- `conv(layer_num, relation, x, edge_index, edge_type)` with the raw edge list
+passed on every call (mp_rgcn_layer.py:158-159) -- reuse one build per graph instead of
+re-filtering the O(E) edge list each forward (mp_rgcn_layer.py:231)."""
+import ctypes
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class RelationGraph:
+    """Owns an `mpgnn_graph` handle: edges bucketed by (relation,row) and (relation,col),
+    stable in original edge order (duplicates kept)."""
+
+    def __init__(self, edge_index, edge_type, num_nodes, num_relations=None, device=None):
+        lib = _lib.load()
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise ValueError("edge_index must be [2, E]")
+        if edge_type is None:
+            raise AssertionError("edge_type is required")  # reference: assert edge_type is not None (:195)
+        if edge_type.numel() != edge_index.size(1):
+            raise ValueError("edge_type must have one entry per edge")
+        if num_relations is None:
+            num_relations = int(edge_type.max().item()) + 1 if edge_type.numel() else 1
+        self.num_nodes, self.num_relations = int(num_nodes), int(num_relations)
+        self.num_edges = int(edge_index.size(1))
+        handle = ctypes.c_void_p()
+        if edge_index.is_cuda:
+            self.device = edge_index.device
+            ei = edge_index.to(torch.int64).contiguous()
+            et = edge_type.to(device=self.device, dtype=torch.int64).contiguous()
+            with torch.cuda.device(self.device):
+                rc = lib.mpgnn_graph_build(_lib.ptr(ei), _lib.ptr(et), self.num_edges, self.num_nodes,
+                                           self.num_relations, _lib.current_stream(), ctypes.byref(handle))
+        else:
+            self.device = torch.device(device if device is not None else "cuda")
+            if self.device.index is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
+            ei = edge_index.to(torch.int64).contiguous()
+            et = edge_type.to(torch.int64).contiguous()
+            with torch.cuda.device(self.device):
+                rc = lib.mpgnn_graph_build_host(ctypes.c_void_p(ei.data_ptr()), ctypes.c_void_p(et.data_ptr()),
+                                                self.num_edges, self.num_nodes, self.num_relations,
+                                                _lib.current_stream(), ctypes.byref(handle))
+        _lib.check(rc)
+        self._handle = handle
+        counts = np.zeros(self.num_relations, dtype=np.int64)
+        _lib.check(lib.mpgnn_graph_relation_counts(self._handle, counts.ctypes.data_as(ctypes.c_void_p)))
+        self.relation_counts = counts
+        self._finalizer = weakref.finalize(self, lib.mpgnn_graph_free, handle)
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def relation_edges(self, relation):
+        return int(self.relation_counts[int(relation)])
+
+    def relation_view(self, relation, transpose=False):
+        """(ptr[N+1], idx[E_r], eid[E_r]) as torch int32 tensors copied out of the handle --
+        for tests and inspection; kernels use the handle directly."""
+        lib = _lib.load()
+        p, i, e = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        n_e = ctypes.c_int64()
+        _lib.check(lib.mpgnn_graph_relation_view(self._handle, int(relation), int(bool(transpose)), ctypes.byref(p),
+                                                 ctypes.byref(i), ctypes.byref(e), ctypes.byref(n_e)))
+        n = self.num_nodes
+        ptr = _device_view(p.value, n + 1, self.device).clone()
+        lo, hi = int(ptr[0].item()), int(ptr[-1].item())
+        assert hi - lo == n_e.value
+        idx = _device_view(i.value + 4 * lo, hi - lo, self.device).clone()
+        eid = _device_view(e.value + 4 * lo, hi - lo, self.device).clone()
+        return ptr - lo, idx, eid
+
+
+def _device_view(addr, count, device):
+    """int32 tensor aliasing `count` elements of device memory at `addr` (no ownership)."""
+    if count == 0:
+        return torch.empty(0, dtype=torch.int32, device=device)
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (addr, True), "version": 3,
+                                  "strides": None}
+    return torch.as_tensor(h, device=device)
+
+
+# ---- cache keyed on the identity of the caller's edge tensors -------------------------------
+_CACHE = {}
+_CACHE_MAX = 8
+
+
+def graph_for(edge_index, edge_type, num_nodes, device):
+    """Return the RelationGraph of (edge_index, edge_type), building it on first use.
+
+    The reference treats edge_index/edge_type as immutable for a run (main.py:1245-1255), so
+    the cache key is the identity of the two tensors (storage pointer, shape, in-place version
+    counter) plus the node count and target device."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_type.data_ptr(),
+           edge_type._version, int(num_nodes), str(device))
+    hit = _CACHE.get(key)
+    if hit is not None:
+        ei_ref, et_ref, g = hit
+        if ei_ref() is edge_index and et_ref() is edge_type:
+            return g
+    # num_relations from the data (reference: relations are whatever ids edge_type holds)
+    g = RelationGraph(edge_index, edge_type, num_nodes, None, device)
+    if len(_CACHE) >= _CACHE_MAX:
+        _CACHE.pop(next(iter(_CACHE)))
+    _CACHE[key] = (weakref.ref(edge_index), weakref.ref(edge_type), g)
+    return g
+
+
+def clear_cache():
+    _CACHE.clear()

@@ -1,0 +1,142 @@
+"""B200-native drop-in for the evaluation-stage calls of the reference's `main.py`
+(main.py:1055-1160): mpgnn_train / mpgnn_validation / mpgnn_test /
+mpgnn_parallel_multiple(_x) keep their names, arguments and return tuples.  `data` is the
+same attribute bag the reference builds at main.py:1245-1255 (x, edge_index, edge_type,
+train_idx, val_idx, test_idx, train_y, val_y, test_y, num_nodes); tensors may live on the
+host (as in the reference) -- they are staged to the model's device once and cached on the
+bag.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .graph import RelationGraph, graph_for
+from .model import MPNetm
+
+EPOCHS_PER_CANDIDATE = 999  # `for epoch in range(1, 1000)` (main.py:1121, 1146)
+ADAM_LR, ADAM_WEIGHT_DECAY = 0.01, 0.0005  # main.py:1119
+
+
+class Data:
+    """Attribute bag standing in for torch_geometric.data.Data (main.py:1245, 1274)."""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def _as_index(v, device):
+    if isinstance(v, torch.Tensor):
+        return v.to(device=device, dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.asarray(v, dtype=np.int64), device=device)
+
+
+def _staged(data, device):
+    """Device copies of the bag's tensors + the relation CSR, built once per (bag, device)."""
+    cache = getattr(data, "_b200_staged", None)
+    if cache is not None and cache["device"] == device and cache["x_src"] is data.x:
+        return cache
+    x = data.x.to(device=device, dtype=torch.float32).contiguous()
+    graph = data.edge_index if isinstance(data.edge_index, RelationGraph) else graph_for(
+        data.edge_index, data.edge_type, x.size(0), device)
+    cache = {"device": device, "x_src": data.x, "x": x, "graph": graph}
+    for split in ("train", "val", "test"):
+        idx = getattr(data, split + "_idx", None)
+        if idx is not None:
+            cache[split + "_idx"] = _as_index(idx, device)
+            cache[split + "_y"] = _as_index(getattr(data, split + "_y"), device)
+    data._b200_staged = cache
+    return cache
+
+
+def _balanced_class_weights(y):
+    """sklearn.utils.class_weight.compute_class_weight('balanced', ...) (main.py:1062): the
+    reference computes and returns it but never uses it."""
+    y = np.asarray(y.cpu() if isinstance(y, torch.Tensor) else y)
+    classes, counts = np.unique(y, return_counts=True)
+    return len(y) / (len(classes) * counts.astype(np.float64))
+
+
+def device_macro_f1(logp, idx, y):
+    """K6: sklearn f1_score(average='macro') of argmax(logp[idx]) vs y, computed on device."""
+    lib = _lib.load()
+    c = logp.size(1)
+    cm = torch.empty(c * c, dtype=torch.int32, device=logp.device)
+    f1 = torch.empty(1, dtype=torch.float64, device=logp.device)
+    with torch.cuda.device(logp.device):
+        _lib.check(lib.mpgnn_macro_f1(_lib.ptr(logp), c, _lib.ptr(idx), _lib.ptr(y), idx.numel(), _lib.ptr(cm),
+                                      _lib.ptr(f1), _lib.current_stream()))
+    return f1
+
+
+def mpgnn_train(model, optimizer, data):
+    """main.py:1055-1082: train-mode forward, nll on the train index, backward, optimiser
+    step.  Returns (float(loss), class_weights)."""
+    st = _staged(data, next(model.parameters()).device)
+    model.train()
+    optimizer.zero_grad()
+    out = model(st["x"], st["graph"])
+    weights = _balanced_class_weights(data.train_y)
+    loss = F.nll_loss(out[st["train_idx"]].squeeze(-1), st["train_y"])
+    loss.backward()
+    optimizer.step()
+    return float(loss), weights
+
+
+@torch.no_grad()
+def mpgnn_validation(model, data, class_weight):
+    """main.py:1084-1100 -> (f1_train, f1_val, f1_val, loss_val); all F1 are macro."""
+    st = _staged(data, next(model.parameters()).device)
+    model.eval()
+    pred = model(st["x"], st["graph"])
+    loss_val = F.nll_loss(pred[st["val_idx"]].squeeze(-1), st["val_y"])
+    f1_train = device_macro_f1(pred, st["train_idx"], st["train_y"])
+    f1_val = device_macro_f1(pred, st["val_idx"], st["val_y"])
+    f1_train, f1_val = float(f1_train.item()), float(f1_val.item())
+    return f1_train, f1_val, f1_val, loss_val
+
+
+@torch.no_grad()
+def mpgnn_test(model, data, class_weight):
+    """main.py:1102-1115 -> (loss_test, f1_test_macro)."""
+    st = _staged(data, next(model.parameters()).device)
+    model.eval()
+    pred = model(st["x"], st["graph"])
+    loss_test = F.nll_loss(pred[st["test_idx"]].squeeze(-1), st["test_y"])
+    f1_test = float(device_macro_f1(pred, st["test_idx"], st["test_y"]).item())
+    return loss_test, f1_test
+
+
+def _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths, epochs):
+    model = MPNetm(input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, len(metapaths), metapaths)
+    optimizer = torch.optim.Adam(model.parameters(), lr=ADAM_LR, weight_decay=ADAM_WEIGHT_DECAY)
+    f1_val = 0.0
+    class_weight = None
+    for _ in range(epochs):
+        _, class_weight = mpgnn_train(model, optimizer, data_mpgnn)
+        _, _, f1_val, _ = mpgnn_validation(model, data_mpgnn, class_weight)
+    return model, class_weight, f1_val
+
+
+def mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,
+                            epochs=EPOCHS_PER_CANDIDATE):
+    """main.py:1117-1134 -- one candidate scored: 999 x (train, validation); returns the LAST
+    epoch's validation macro-F1."""
+    _, _, f1_val = _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
+                                    metapaths, epochs)
+    return f1_val
+
+
+def mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,
+                              testing, epochs=EPOCHS_PER_CANDIDATE):
+    """main.py:1136-1160 -- same for a list of metapaths; returns test macro-F1 if `testing`."""
+    if isinstance(metapaths[0], (int, np.integer)):
+        metapaths = [metapaths]
+    model, class_weight, f1_val = _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim,
+                                                   ll_output_dim, metapaths, epochs)
+    test_loss, f1_test = mpgnn_test(model, data_mpgnn, class_weight)
+    print("test loss %0.3f" % test_loss, "test macro %0.3f" % f1_test)
+    return f1_test if testing else f1_val
