@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Bench of the MPGNN hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K ...   (CPU arm: the oracle port of the
+                                                               reference's torch-CPU path)
+
+Workload (BASELINE.json configs[3], the largest single-GPU configuration, "C4"): synthetic
+heterogeneous graph, 10M nodes / 200M edges / 64 relations, feature and hidden width 128.
+A "step" is one metapath hop, forward + backward, of the MP-RGCN layer over ONE relation
+(CustomRGCNConv.forward + relu + dropout(0.6) and everything autograd derives for it,
+including the input gradient); successive steps walk the relations, so a 64-step run is
+the full 64-relation sweep.  metric = metapath-hop edges/s = sum of E_r over the timed
+steps / time.  x (5.12 GB) is far larger than the 126 MB L2, so no flush is needed.
+
+N > 1: every rank holds the replicated graph and runs its own hops (different relations),
+as the candidate fan-out does; no data-path collective; value = all ranks' edges / max time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "metapath_hop_edges_per_s_mp_rgcn_fwd_bwd"
+UNIT = "edges/s"
+DROPOUT_P = 0.6
+
+WORKLOADS = {
+    # name: (nodes, edges, relations, feat)
+    "c4": (10_000_000, 200_000_000, 64, 128),
+    "c4_tenth": (1_000_000, 20_000_000, 64, 128),   # CPU-arm sample of the same shape
+    "tiny": (20_000, 400_000, 8, 128),              # plumbing check only
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(n, e_r, f):
+    """SURVEY.md section 8(d), fp32 values / int32 indices, gathers counted without reuse."""
+    return {
+        "spmm_mean_fwd": 4 * (e_r * (f + 1) + n * f + (n + 1)),
+        "layer_fwd_fused": 4 * (n * (f + f) + e_r * (f + 1) + (n + 1)),
+        "layer_bwd": 4 * (n * (2 * f + 2 * f) + e_r * (2 * f + 2) + 2 * (n + 1)),
+        "spmm_transpose_bwd": 4 * (e_r * (f + 1) + 2 * n * f + (n + 1)),
+    }
+
+
+def run_ours(args):
+    import mpgnn_b200
+    from mpgnn_b200 import _lib
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    n, e, r, f = WORKLOADS[args.workload]
+    precision = args.precision
+
+    # ---- synthetic graph of the named shape (seed 0), built once: the graph is a run constant
+    gen = torch.Generator(device=dev).manual_seed(0)
+    ei = torch.randint(0, n, (2, e), device=dev, generator=gen)
+    et = torch.randint(0, r, (e,), device=dev, generator=gen)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    graph = mpgnn_b200.RelationGraph(ei, et, n, r)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    del ei, et
+    torch.cuda.empty_cache()
+    x = torch.randn(n, f, device=dev, generator=gen)
+    gy = torch.randn(n, f, device=dev, generator=gen)
+    torch.manual_seed(30)
+    conv = mpgnn_b200.CustomRGCNConv(f, f, 1, flow="target_to_source", device=dev)
+    w, root, bias = conv.weight.detach(), conv.root.detach(), conv.bias.detach()
+    h = torch.empty(n, f, device=dev)
+    y = torch.empty(n, f, device=dev)
+    gx = torch.empty(n, f, device=dev)
+    gw, groot, gb = torch.empty_like(w), torch.empty_like(root), torch.empty_like(bias)
+    ws = torch.empty(lib.mpgnn_hop_workspace_bytes(n, f, f), dtype=torch.uint8, device=dev)
+    flags_f = _lib.F_RELU | _lib.F_DROPOUT_SEED
+    if precision == "tf32x3":
+        flags_f |= _lib.F_TF32X3
+    elif precision == "bf16":
+        flags_f |= _lib.F_BF16
+    flags_b = flags_f | _lib.F_NEED_GX
+    stream = _lib.current_stream()
+
+    def hop(step, x_dev):
+        rel = (step * world + rank) % r
+        _lib.check(lib.mpgnn_hop_fwd(graph.handle, rel, _lib.ptr(x_dev), f, _lib.ptr(w), _lib.ptr(root),
+                                     _lib.ptr(bias), f, flags_f, DROPOUT_P, 1234, step, None, _lib.ptr(h),
+                                     _lib.ptr(y), _lib.ptr(ws), ws.numel(), stream))
+        _lib.check(lib.mpgnn_hop_bwd(graph.handle, rel, _lib.ptr(x_dev), _lib.ptr(h), _lib.ptr(y), _lib.ptr(gy), f,
+                                     _lib.ptr(w), _lib.ptr(root), f, flags_b, DROPOUT_P, _lib.ptr(gx), _lib.ptr(gw),
+                                     _lib.ptr(groot), _lib.ptr(gb), _lib.ptr(ws), ws.numel(), stream))
+        return graph.relation_edges(rel)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, first_step):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        edges = 0
+        for s in range(steps):
+            edges += fn(first_step + s)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ed = torch.tensor([edges], device=dev, dtype=torch.float64)
+            dist.all_reduce(ed, op=dist.ReduceOp.SUM)
+            ms, edges = float(t.item()), float(ed.item())
+        return ms, edges
+
+    # ---- device-resident arm ------------------------------------------------------------
+    for s in range(args.warmup):
+        hop(s, x)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.mpgnn_launch_count()
+    ms, edges = timed(lambda s: hop(s, x), args.steps, args.warmup)
+    launches = lib.mpgnn_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = edges / (ms * 1e-3)
+
+    # ---- per-kernel-class breakdown (separate pass, CUDA events on the launching stream) --
+    lib.mpgnn_timing_reset()
+    lib.mpgnn_timing_enable(1)
+    e_sum = 0
+    for s in range(args.steps):
+        e_sum += hop(args.warmup + s, x)
+    torch.cuda.synchronize()
+    lib.mpgnn_timing_enable(0)
+    kern = _lib.timing_collect()
+    e_r_mean = e_sum / args.steps
+
+    # ---- end-to-end arm: host (pinned) features in, gradients + a loss scalar out ---------
+    e2e = None
+    if not args.no_e2e:
+        x_host = torch.empty(n, f, dtype=torch.float32).pin_memory()
+        x_host.copy_(x)
+        x_stage = torch.empty_like(x)
+        out_host = torch.empty(2 * f * f + f + 1, dtype=torch.float32).pin_memory()
+        out_dev = torch.empty(2 * f * f + f + 1, device=dev)
+
+        def e2e_step(s):
+            x_stage.copy_(x_host, non_blocking=True)         # H2D of the step's input features
+            ed = hop(s, x_stage)
+            out_dev[:f * f].copy_(gw.view(-1))
+            out_dev[f * f:2 * f * f].copy_(groot.view(-1))
+            out_dev[2 * f * f:2 * f * f + f].copy_(gb)
+            out_dev[-1:] = y[0, :1]
+            out_host.copy_(out_dev, non_blocking=True)       # D2H of the step's result
+            torch.cuda.current_stream().synchronize()        # the caller reads the result
+            return ed
+
+        for s in range(2):
+            e2e_step(s)
+        e_steps = max(3, min(args.steps, 10))
+        ms_e, edges_e = timed(e2e_step, e_steps, args.warmup)
+        e2e = {"value": edges_e / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+               "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e_steps,
+               "ms_per_step": ms_e / e_steps}
+
+    if rank != 0:
+        return
+    hbm, tf, how = _peaks()
+    ab = algorithmic_bytes(n, e_r_mean, f)
+    per_kernel = {}
+    total_ms = sum(v[0] for v in kern.values()) or 1.0
+    for k, (kms, calls) in kern.items():
+        per_kernel[k] = {"ms_per_launch": kms / max(calls, 1), "share": kms / total_ms, "calls": calls}
+    dominant = max(kern, key=lambda k: kern[k][0]) if kern else None
+    flops_proj = 2.0 * n * (2 * f) * f
+    roofline = None
+    if dominant is not None:
+        d_ms = per_kernel[dominant]["ms_per_launch"]
+        if dominant.startswith("spmm"):
+            byts = ab[dominant]
+            roofline = {"kernel": dominant, "bound": "hbm", "achieved": byts / (d_ms * 1e-3) / 1e9, "peak": hbm,
+                        "unit": "GB/s", "traffic": None, "algorithmic_bytes": byts}
+        elif dominant == "relu_dropout_bwd":
+            byts = 3 * 4 * n * f
+            roofline = {"kernel": dominant, "bound": "hbm", "achieved": byts / (d_ms * 1e-3) / 1e9, "peak": hbm,
+                        "unit": "GB/s", "traffic": None, "algorithmic_bytes": byts}
+        else:  # dense contractions: [N,2F]x[2F,F] each
+            roofline = {"kernel": dominant, "bound": "tensor", "achieved": flops_proj / (d_ms * 1e-3) / 1e12,
+                        "peak": tf, "unit": "TFLOP/s", "traffic": None, "algorithmic_flops": flops_proj}
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        roofline["peak_source"] = how
+    # the north-star kernel is always reported next to the dominant one
+    spmm_roof = None
+    if "spmm_mean_fwd" in per_kernel:
+        s_ms = per_kernel["spmm_mean_fwd"]["ms_per_launch"]
+        spmm_roof = {"achieved_gbs": ab["spmm_mean_fwd"] / (s_ms * 1e-3) / 1e9, "peak_gbs": hbm,
+                     "frac": ab["spmm_mean_fwd"] / (s_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": ab["spmm_mean_fwd"]}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(steps=3, warmup=1, budget_s=30.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if precision == "fp32" else precision, "data": "synthetic",
+        "config": {"workload": "C4: %d nodes / %d edges / %d relations / hidden %d; step = 1 metapath hop fwd+bwd "
+                               "(relu + dropout 0.6 fused, input gradient included), relations cycled" % (n, e, r, f),
+                   "l2": "inputs (5.12 GB per dense operand) larger than L2, no flush", "precision": precision,
+                   "parallelism": "replicated graph, hops sharded by relation over %d GPU(s)" % world},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "extra": {"graph_build_s": build_s, "rows_per_s": n * args.steps * world / (ms * 1e-3),
+                  "mean_edges_per_hop": e_r_mean, "kernels": per_kernel, "spmm_mean_fwd_roofline": spmm_roof},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(steps, warmup, budget_s, workload="c4_tenth"):
+    """The reference's CPU path for the same step (oracle port: relation filter O(E), PyG
+    scatter-mean, two mm, autograd-equivalent backward) on the host cores, on a bounded
+    sample: the C4 shape at 1/10 scale (1M nodes / 20M edges / 64 relations / hidden 128)."""
+    from oracle import mpgnn_oracle as orc
+    n, e, r, f = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    et = torch.randint(0, r, (e,), generator=g)
+    x = torch.randn(n, f, generator=g)
+    gy = torch.randn(n, f, generator=g)
+    torch.manual_seed(30)
+    p = orc.conv_init(f, f)
+
+    def step(s):
+        rel = s % r
+        z, h, cnt = orc.conv_forward(x, ei, et, rel, p["weight"], p["root"], p["bias"])
+        keep = (torch.rand(n, f) >= DROPOUT_P).float()
+        yv = torch.relu(z) * keep * 2.5
+        gz = gy * (yv > 0) * 2.5
+        orc.conv_backward(x, ei, et, rel, p["weight"], p["root"], h, cnt, gz, need_gx=True)
+        return int((et == rel).sum())
+
+    for s in range(warmup):
+        step(s)
+    t0 = time.time()
+    edges, done = 0, 0
+    for s in range(steps):
+        edges += step(warmup + s)
+        done += 1
+        if time.time() - t0 > budget_s:
+            break
+    dt = time.time() - t0
+    return {"value": edges / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "C4 shape at 1/10 scale (%d nodes / %d edges / %d relations / hidden %d), %d hop(s) fwd+bwd, "
+                      "torch-CPU %d threads" % (n, e, r, f, done, cores), "ms_per_step": dt / done * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, e, r, f = WORKLOADS["c4"]
+    cpu = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1), budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4: %d nodes / %d edges / %d relations / hidden %d; step = 1 metapath hop fwd+bwd; "
+                               "CPU arm runs a bounded sample of it" % (n, e, r, f)},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for "
+                             "the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

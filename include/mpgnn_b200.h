@@ -40,6 +40,16 @@ typedef struct mpgnn_graph mpgnn_graph; /* relation-typed CSR + CSC, device resi
 const char* mpgnn_last_error(void);
 int mpgnn_abi_version(void);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------
+ * mpgnn_launch_count: kernels launched by this library so far in this process.
+ * mpgnn_timing_*: optional CUDA-event timing of each kernel class on its launching stream;
+ * collect() synchronises on the recorded events and returns the number of classes, their
+ * ';'-separated names, accumulated milliseconds and call counts. */
+long long mpgnn_launch_count(void);
+void mpgnn_timing_enable(int on);
+void mpgnn_timing_reset(void);
+int mpgnn_timing_collect(char* names, int64_t names_bytes, double* ms, int64_t* calls, int64_t capacity);
+
 /* ---- K1: relation-typed CSR/CSC construction ------------------------------------------
  * Replaces the per-call O(E) filter `masked_edge_index(edge_index, edge_type == relation)`
  * (mp_rgcn_layer.py:29-37, call site :231) and the scatter index PyG derives from it:

@@ -18,6 +18,10 @@ _i64, _i32, _u32, _u64, _dbl, _ptr = _c.c_int64, _c.c_int, _c.c_uint32, _c.c_uin
 PROTOTYPES = {
     "mpgnn_last_error": (_c.c_char_p, []),
     "mpgnn_abi_version": (_i32, []),
+    "mpgnn_launch_count": (_c.c_longlong, []),
+    "mpgnn_timing_enable": (None, [_i32]),
+    "mpgnn_timing_reset": (None, []),
+    "mpgnn_timing_collect": (_i32, [_c.c_char_p, _i64, _ptr, _ptr, _i64]),
     "mpgnn_graph_build": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _c.POINTER(_ptr)]),
     "mpgnn_graph_build_host": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _c.POINTER(_ptr)]),
     "mpgnn_graph_free": (None, [_ptr]),
@@ -86,3 +90,16 @@ def current_stream():
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def timing_collect():
+    """{kernel class: (milliseconds, calls)} accumulated since the last timing_reset()."""
+    import numpy as np
+    lib = load()
+    names = ctypes.create_string_buffer(4096)
+    ms = np.zeros(64, dtype=np.float64)
+    calls = np.zeros(64, dtype=np.int64)
+    n = lib.mpgnn_timing_collect(names, 4096, ms.ctypes.data_as(ctypes.c_void_p), calls.ctypes.data_as(ctypes.c_void_p),
+                                 64)
+    keys = [k for k in names.value.decode().split(";") if k][:n]
+    return {k: (float(ms[i]), int(calls[i])) for i, k in enumerate(keys)}

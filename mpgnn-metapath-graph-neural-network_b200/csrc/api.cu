@@ -14,6 +14,60 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- launch counter + optional event timing ------------------------------------------------
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+constexpr int kMaxTimerSlots = 32;
+constexpr int kMaxTimerEvents = 4096;
+static bool g_timing = false;
+static int g_n_slots = 0;
+static char g_slot_names[kMaxTimerSlots][48];
+static double g_slot_ms[kMaxTimerSlots];
+static long long g_slot_calls[kMaxTimerSlots];
+static cudaEvent_t g_ev_start[kMaxTimerEvents], g_ev_stop[kMaxTimerEvents];
+static int g_ev_slot[kMaxTimerEvents];
+static int g_n_events = 0, g_n_events_created = 0;
+
+ScopedTimer::ScopedTimer(const char* name, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_timing || g_n_events >= kMaxTimerEvents) return;
+  int k = 0;
+  for (; k < g_n_slots; ++k)
+    if (strncmp(g_slot_names[k], name, 47) == 0) break;
+  if (k == g_n_slots) {
+    if (g_n_slots >= kMaxTimerSlots) return;
+    strncpy(g_slot_names[k], name, 47);
+    g_slot_names[k][47] = 0;
+    g_slot_ms[k] = 0.0;
+    g_slot_calls[k] = 0;
+    ++g_n_slots;
+  }
+  if (g_n_events >= g_n_events_created) {
+    cudaEventCreate(&g_ev_start[g_n_events]);
+    cudaEventCreate(&g_ev_stop[g_n_events]);
+    ++g_n_events_created;
+  }
+  slot = g_n_events++;
+  g_ev_slot[slot] = k;
+  cudaEventRecord(g_ev_start[slot], stream);
+}
+
+ScopedTimer::~ScopedTimer() {
+  if (slot >= 0) cudaEventRecord(g_ev_stop[slot], stream);
+}
+
+static void timing_flush() {
+  for (int i = 0; i < g_n_events; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_ev_stop[i]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, g_ev_start[i], g_ev_stop[i]) == cudaSuccess) {
+      g_slot_ms[g_ev_slot[i]] += ms;
+      g_slot_calls[g_ev_slot[i]] += 1;
+    }
+  }
+  g_n_events = 0;
+}
+
 int graph_build_device(const int64_t* d_edge_index, const int64_t* d_edge_type, int64_t e, int64_t n, int64_t r,
                        cudaStream_t s, mpgnn_graph_impl** out);
 void graph_free(mpgnn_graph_impl* g);
@@ -46,6 +100,36 @@ extern "C" {
 const char* mpgnn_last_error(void) { return g_error; }
 
 int mpgnn_abi_version(void) { return 1; }
+
+long long mpgnn_launch_count(void) { return g_launches; }
+
+void mpgnn_timing_enable(int on) {
+  timing_flush();
+  g_timing = on != 0;
+}
+
+void mpgnn_timing_reset(void) {
+  timing_flush();
+  g_n_slots = 0;
+}
+
+int mpgnn_timing_collect(char* names, int64_t names_bytes, double* ms, int64_t* calls, int64_t capacity) {
+  timing_flush();
+  int64_t used = 0;
+  int n = 0;
+  for (int k = 0; k < g_n_slots && k < capacity; ++k) {
+    const int64_t len = (int64_t)strlen(g_slot_names[k]);
+    if (used + len + 2 > names_bytes) break;
+    memcpy(names + used, g_slot_names[k], (size_t)len);
+    used += len;
+    names[used++] = ';';
+    ms[k] = g_slot_ms[k];
+    calls[k] = g_slot_calls[k];
+    ++n;
+  }
+  if (names_bytes > 0) names[used < names_bytes ? used : names_bytes - 1] = 0;
+  return n;
+}
 
 int mpgnn_graph_build(const int64_t* d_edge_index, const int64_t* d_edge_type, int64_t num_edges, int64_t num_nodes,
                       int64_t num_relations, void* stream, mpgnn_graph** out) {

@@ -10,6 +10,16 @@
 namespace mpgnn {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+
+// Optional per-kernel-class CUDA-event timing on the launching stream (mpgnn_timing_*):
+// off by default; bench.py enables it for a separate breakdown pass.
+struct ScopedTimer {
+  int slot;
+  cudaStream_t stream;
+  ScopedTimer(const char* name, cudaStream_t s);
+  ~ScopedTimer();
+};
 
 #define MPGNN_CUDA_CHECK(expr)                                                                      \
   do {                                                                                              \
@@ -20,7 +30,12 @@ void set_error(const char* fmt, ...);
     }                                                                                               \
   } while (0)
 
-#define MPGNN_LAUNCH_CHECK() MPGNN_CUDA_CHECK(cudaGetLastError())
+// every kernel launch site goes through this: counts the launch (bench.py's gpu_launches)
+#define MPGNN_LAUNCH_CHECK()                 \
+  do {                                       \
+    mpgnn::count_launch();                   \
+    MPGNN_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
 
 #define MPGNN_REQUIRE(cond, code, ...)   \
   do {                                   \

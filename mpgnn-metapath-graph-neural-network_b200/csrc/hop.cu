@@ -36,7 +36,10 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   MPGNN_REQUIRE(bp != nullptr, MPGNN_EINVAL, "hop_fwd: workspace too small");
 
   const int32_t* ptr = g->csr_ptr + rel * g->n;
-  MPGNN_PROPAGATE(launch_spmm(ptr, g->csr_idx, g->n, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));
+  {
+    ScopedTimer tm("spmm_mean_fwd", s);
+    MPGNN_PROPAGATE(launch_spmm(ptr, g->csr_idx, g->n, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));
+  }
   MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp, w, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
   MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp + f_in * f_out, root, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
 
@@ -49,8 +52,11 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   a.dropout_mode = drop_seed ? 1 : (drop_mask ? 2 : 0);
   a.dropout_p = (float)p; a.dropout_scale = (float)(1.0 / (1.0 - p)); a.seed = seed; a.offset = offset; a.mask_bits = mask_bits;
   a.out = y; a.ldo = f_out;
-  if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags))
+  if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
+    ScopedTimer tm("proj_fwd_tcgen05", s);
     return launch_proj_tcgen05(a, flags, s);
+  }
+  ScopedTimer tm("proj_fwd_simt", s);
   return launch_gemm_rows(a, s);
 }
 
@@ -76,6 +82,7 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   const float* gz_src = gy;
   if (flags & MPGNN_F_RELU) {
     const float scale = drop ? (float)(1.0 / (1.0 - p)) : 1.f;
+    ScopedTimer tm("relu_dropout_bwd", s);
     MPGNN_PROPAGATE(launch_relu_dropout_bwd(gy, y, scale, gz, n * f_out, s));
     gz_src = gz;
   }
@@ -88,7 +95,10 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   tn.out2 = groot; tn.ldo2 = f_out;
   tn.out_ones = gbias;
   tn.partials = partials; tn.partial_capacity_floats = part_floats;
-  MPGNN_PROPAGATE(launch_gemm_tn(tn, s));
+  {
+    ScopedTimer tm("wgrad_tn_simt", s);
+    MPGNN_PROPAGATE(launch_gemm_tn(tn, s));
+  }
 
   if (need_gx) {
     // [t | g_z root^T] = g_z @ [W^T | root^T], first f_in columns divided by deg_r(row)
@@ -100,8 +110,12 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
     a.b = bp2; a.m = n; a.n = 2 * f_in;
     a.deg_ptr = g->csr_ptr + rel * n; a.deg_cols = f_in;
     a.out = t; a.ldo = 2 * f_in;
-    MPGNN_PROPAGATE(launch_gemm_rows(a, s));
+    {
+      ScopedTimer tm("dgrad_nt_simt", s);
+      MPGNN_PROPAGATE(launch_gemm_rows(a, s));
+    }
     // g_x[j] = (g_z root^T)[j] + sum_{e: col(e)=j} t[row(e)]
+    ScopedTimer tm("spmm_transpose_bwd", s);
     MPGNN_PROPAGATE(launch_spmm(g->csc_ptr + rel * n, g->csc_idx, n, /*mean=*/0, t, 2 * f_in, f_in, t + f_in,
                                 2 * f_in, gx, f_in, s));
   }

@@ -85,7 +85,7 @@ def _device_view(addr, count, device):
         pass
 
     h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (addr, True), "version": 3,
+    h.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i4", "data": (addr, False), "version": 3,
                                   "strides": None}
     return torch.as_tensor(h, device=device)
 
