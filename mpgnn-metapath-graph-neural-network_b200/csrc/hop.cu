@@ -6,9 +6,13 @@
 namespace mpgnn {
 
 int proj_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags);
-int launch_proj_tcgen05(const GemmRowsArgs& a, uint32_t flags, cudaStream_t s);
+int64_t proj_tcgen05_workspace_floats(int64_t k, int64_t n);
+int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, cudaStream_t s);
 
-static int64_t fwd_ws_floats(int64_t f_in, int64_t f_out) { return align_up(2 * f_in * f_out, 64); }
+// packed [W;root] followed by its hi/lo UMMA images for the tensor-core path
+static int64_t fwd_ws_floats(int64_t f_in, int64_t f_out) {
+  return align_up(2 * f_in * f_out, 64) + align_up(proj_tcgen05_workspace_floats(2 * f_in, f_out), 64);
+}
 
 int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
   int64_t floats = 0;
@@ -16,6 +20,7 @@ int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
   floats += align_up(n * f_out, 64);                                   // g_z
   floats += align_up(gemm_tn_partial_floats(n, 2 * f_in + 1, f_out), 64);  // split-K partials
   floats += align_up(f_out * 2 * f_in, 64);                            // packed [W^T | root^T]
+  floats += align_up(proj_tcgen05_workspace_floats(f_out, 2 * f_in), 64);  // its hi/lo UMMA images
   floats += align_up(n * 2 * f_in, 64);                                // [t | g_z root^T]
   return floats * 4 + 8 * 256;
 }
@@ -54,7 +59,7 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   a.out = y; a.ldo = f_out;
   if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
     ScopedTimer tm("proj_fwd_tcgen05", s);
-    return launch_proj_tcgen05(a, flags, s);
+    return launch_proj_tcgen05_ws(a, flags, bp + align_up(2 * f_in * f_out, 64), s);
   }
   ScopedTimer tm("proj_fwd_simt", s);
   return launch_gemm_rows(a, s);
@@ -76,8 +81,9 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   const int64_t part_floats = gemm_tn_partial_floats(n, 2 * f_in + 1, f_out);
   float* partials = ws.take<float>(align_up(part_floats, 64));
   float* bp2 = ws.take<float>(align_up(f_out * 2 * f_in, 64));
+  float* bp2_img = ws.take<float>(align_up(proj_tcgen05_workspace_floats(f_out, 2 * f_in), 64));
   float* t = need_gx ? ws.take<float>(align_up(n * 2 * f_in, 64)) : nullptr;
-  MPGNN_REQUIRE(gz && partials && bp2 && (!need_gx || t), MPGNN_EINVAL, "hop_bwd: workspace too small");
+  MPGNN_REQUIRE(gz && partials && bp2 && bp2_img && (!need_gx || t), MPGNN_EINVAL, "hop_bwd: workspace too small");
 
   const float* gz_src = gy;
   if (flags & MPGNN_F_RELU) {
@@ -110,7 +116,10 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
     a.b = bp2; a.m = n; a.n = 2 * f_in;
     a.deg_ptr = g->csr_ptr + rel * n; a.deg_cols = f_in;
     a.out = t; a.ldo = 2 * f_in;
-    {
+    if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
+      ScopedTimer tm("dgrad_nt_tcgen05", s);
+      MPGNN_PROPAGATE(launch_proj_tcgen05_ws(a, flags, bp2_img, s));
+    } else {
       ScopedTimer tm("dgrad_nt_simt", s);
       MPGNN_PROPAGATE(launch_gemm_rows(a, s));
     }

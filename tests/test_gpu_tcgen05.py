@@ -1,0 +1,119 @@
+"""tcgen05 (3xTF32) projection path against the exact-fp32 SIMT path and the oracle.
+Bar: normalised max error <= 1e-5 (the fp32 parity bar of the north star).
+
+The backward is compared on IDENTICAL saved tensors (x, h, y of one forward): ReLU is
+discontinuous, so two fp32-accurate forwards may legitimately disagree on the sign of a
+pre-activation that is ~1e-7 from zero, which would flip a whole gradient row."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import mpgnn_oracle as orc
+
+import mpgnn_b200
+from mpgnn_b200 import _lib
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
+DEV = "cuda"
+TOL = 1e-5
+
+
+def _graph(n, e, r, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (2, e), generator=g), torch.randint(0, r, (e,), generator=g)
+
+
+def _fwd(graph, rel, x, w, root, b, flags, mask_bits):
+    lib = _lib.load()
+    n, f_in = x.shape
+    f_out = w.size(1)
+    h = torch.empty(n, f_in, device=DEV)
+    y = torch.empty(n, f_out, device=DEV)
+    ws = torch.empty(lib.mpgnn_hop_workspace_bytes(n, f_in, f_out), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.mpgnn_hop_fwd(graph.handle, rel, _lib.ptr(x), f_in, _lib.ptr(w), _lib.ptr(root), _lib.ptr(b), f_out,
+                                 flags, 0.6, 0, 0, _lib.ptr(mask_bits), _lib.ptr(h), _lib.ptr(y), _lib.ptr(ws),
+                                 ws.numel(), _lib.current_stream()))
+    torch.cuda.synchronize()
+    return h, y
+
+
+def _bwd(graph, rel, x, h, y, gy, w, root, flags):
+    lib = _lib.load()
+    n, f_in = x.shape
+    f_out = w.size(1)
+    gx = torch.empty(n, f_in, device=DEV)
+    gw, gr, gb = torch.empty_like(w), torch.empty_like(root), torch.empty(f_out, device=DEV)
+    ws = torch.empty(lib.mpgnn_hop_workspace_bytes(n, f_in, f_out), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.mpgnn_hop_bwd(graph.handle, rel, _lib.ptr(x), _lib.ptr(h), _lib.ptr(y), _lib.ptr(gy), f_in,
+                                 _lib.ptr(w), _lib.ptr(root), f_out, flags | _lib.F_NEED_GX, 0.6, _lib.ptr(gx),
+                                 _lib.ptr(gw), _lib.ptr(gr), _lib.ptr(gb), _lib.ptr(ws), ws.numel(),
+                                 _lib.current_stream()))
+    torch.cuda.synchronize()
+    return gx, gw, gr, gb
+
+
+@pytest.mark.parametrize("n,f_in,f_out", [(128, 64, 64), (1000, 64, 64), (5000, 128, 128), (40000, 128, 128),
+                                          (19001, 64, 128), (3000, 32, 64), (2500, 128, 64), (50001, 96, 192)])
+def test_hop_tf32x3_matches_fp32_paths(n, f_in, f_out):
+    from mpgnn_b200.mp_rgcn_layer import pack_mask_bits
+    e, r = 6 * n, 3
+    ei, et = _graph(n, e, r, seed=n)
+    gen = torch.Generator().manual_seed(n + 1)
+    x = torch.randn(n, f_in, generator=gen)
+    gy = torch.randn(n, f_out, generator=gen).to(DEV)
+    mask = (torch.rand(n, f_out, generator=gen) > 0.6).float()
+    torch.manual_seed(n)
+    p = orc.conv_init(f_in, f_out)
+    w, root = p["weight"], p["root"]
+    b = torch.randn(f_out, generator=gen) * 0.1
+    graph = mpgnn_b200.RelationGraph(ei, et, n, r, device=DEV)
+    xd, wd, rd, bd = x.to(DEV), w.to(DEV), root.to(DEV), b.to(DEV)
+    bits = pack_mask_bits(mask.to(DEV))
+    base = _lib.F_RELU | _lib.F_DROPOUT_MASK
+    h32, y32 = _fwd(graph, 1, xd, wd, rd, bd, base, bits)
+    htc, ytc = _fwd(graph, 1, xd, wd, rd, bd, base | _lib.F_TF32X3, bits)
+    assert torch.equal(h32, htc)
+    assert rel_err(ytc, y32) < TOL
+    z, h, cnt = orc.conv_forward(x, ei, et, 1, w, root, b)
+    assert rel_err(ytc, torch.relu(z) * mask * 2.5) < TOL
+    g32 = _bwd(graph, 1, xd, h32, y32, gy, wd, rd, base)
+    gtc = _bwd(graph, 1, xd, h32, y32, gy, wd, rd, base | _lib.F_TF32X3)
+    for a, c in zip(gtc, g32):
+        assert rel_err(a, c) < TOL
+    # oracle backward on the same activation pattern (y32 > 0)
+    gz = gy.cpu() * (y32.cpu() > 0) * 2.5
+    gx_ref, gw_ref, gr_ref, gb_ref = orc.conv_backward(x, ei, et, 1, w, root, h, cnt, gz)
+    for a, c in zip(gtc, (gx_ref, gw_ref, gr_ref, gb_ref)):
+        assert rel_err(a, c) < TOL
+
+
+def test_hop_tf32x3_seeded_dropout_same_stream_as_fp32():
+    n, f = 3000, 128
+    ei, et = _graph(n, 20000, 2, seed=1)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 2, device=DEV)
+    conv = mpgnn_b200.CustomRGCNConv(f, f, 1, flow="target_to_source", device=DEV)
+    x = torch.randn(n, f, device=DEV)
+    with torch.no_grad():
+        a = conv.hop(0, x, graph, dropout_p=0.6, seed=77, offset=3, precision="fp32")
+        b = conv.hop(0, x, graph, dropout_p=0.6, seed=77, offset=3, precision="tf32x3")
+    assert torch.equal(a != 0, b != 0)          # same keep decisions from the counter RNG
+    assert rel_err(b, a) < TOL
+
+
+def test_tf32x3_accuracy_is_fp32_class():
+    """The split must beat plain TF32 by orders of magnitude: compare with a float64 product."""
+    n, f = 8192, 128
+    ei, et = _graph(n, 4 * n, 1, seed=2)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 1, device=DEV)
+    conv = mpgnn_b200.CustomRGCNConv(f, f, 1, flow="target_to_source", device=DEV)
+    x = torch.randn(n, f, device=DEV) * 3.0
+    with torch.no_grad():
+        y = conv.hop(0, x, graph, precision="tf32x3")
+        h = torch.zeros(n, f, dtype=torch.float64, device=DEV)
+        cnt = torch.zeros(n, dtype=torch.float64, device=DEV)
+        rows, cols = ei[0].to(DEV), ei[1].to(DEV)
+        h.index_add_(0, rows, x.double()[cols])
+        cnt.index_add_(0, rows, torch.ones(rows.numel(), dtype=torch.float64, device=DEV))
+        ref = (h / cnt.clamp(min=1).unsqueeze(1)) @ conv.weight.double() + x.double() @ conv.root.double() \
+            + conv.bias.double()
+    assert rel_err(y, ref) < 2e-6
