@@ -101,6 +101,7 @@ struct GemmRowsArgs {
   int64_t deg_cols;            // out[:, :deg_cols] /= max(1,deg)
   int dropout_mode;            // 0 none, 1 seed, 2 mask bits
   float dropout_p; float dropout_scale;   // scale = (float)(1/(1-p)) formed in double on the host
+  uint32_t dropout_thr16;                 // keep iff 16-bit random lane >= thr16 = round(p*65536)
   uint64_t seed; uint64_t offset; const uint8_t* mask_bits;
   float* out; int64_t ldo;
 };
@@ -129,36 +130,27 @@ int launch_spmm(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean
                 int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s);
 
 // ---- device helpers ---------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
-  *hi = __umulhi(a, b);
-  return a * b;
+// Counter-based dropout randomness: one 64-bit SplitMix64-mixed word per block of 4 consecutive
+// output elements (elem >> 2), keyed by (seed, offset).  Stateless, so the stream does not depend
+// on the launch geometry and both projection paths (SIMT / tcgen05) draw identical masks.  Element
+// j of the block keeps its value iff its 16-bit lane >= thr16 = round(p * 65536).
+__device__ __forceinline__ uint64_t dropout_word(uint64_t seed, uint64_t offset, uint64_t blk) {
+  uint64_t z = blk * 0x9E3779B97F4A7C15ull + (seed ^ (offset * 0xD1B54A32D192ED03ull));
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
 }
 
-// Philox4x32-10 (Salmon et al. 2011): counter-based, so the backward never needs the mask
-// stored and the stream does not depend on the launch geometry.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0, hi1;
-    uint32_t lo0 = mulhilo32(M0, ctr.x, &hi0);
-    uint32_t lo1 = mulhilo32(M1, ctr.z, &hi1);
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t elem, uint32_t thr16) {
+  const uint64_t w = dropout_word(seed, offset, elem >> 2);
+  return (uint32_t)((w >> (16 * (elem & 3))) & 0xFFFFu) >= thr16;
 }
 
-// keep-decision of output element `elem` (row*F+col) under (seed, offset): one Philox call
-// covers 4 consecutive elements; u in [0,1) from the top 24 bits, keep iff u >= p.
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t elem, float p) {
-  uint64_t blk = elem >> 2;
-  uint4 ctr = make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)offset, (uint32_t)(offset >> 32));
-  uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  uint32_t lane = (uint32_t)(elem & 3);
-  uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
-  return (float)(v >> 8) * (1.0f / 16777216.0f) >= p;
+static inline uint32_t dropout_threshold16(double p) {
+  double t = p * 65536.0 + 0.5;
+  if (t < 0) t = 0;
+  if (t > 65535.0) t = 65535.0;
+  return (uint32_t)t;
 }
 
 }  // namespace mpgnn

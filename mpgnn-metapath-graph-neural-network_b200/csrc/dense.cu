@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.gate != nullptr) v = (__ldg(a.gate + row * a.ldgate + col) > 0.f) ? v : 0.f;
       if (a.dropout_mode == 1) {
-        v = dropout_keep(a.seed, a.offset, (uint64_t)row * (uint64_t)a.n + (uint64_t)col, a.dropout_p) ? v * scale : 0.f;
+        v = dropout_keep(a.seed, a.offset, (uint64_t)row * (uint64_t)a.n + (uint64_t)col, a.dropout_thr16) ? v * scale : 0.f;
       } else if (a.dropout_mode == 2) {
         const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
         v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;

@@ -55,7 +55,8 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   a.bias = bias;
   a.relu = (flags & MPGNN_F_RELU) ? 1 : 0;
   a.dropout_mode = drop_seed ? 1 : (drop_mask ? 2 : 0);
-  a.dropout_p = (float)p; a.dropout_scale = (float)(1.0 / (1.0 - p)); a.seed = seed; a.offset = offset; a.mask_bits = mask_bits;
+  a.dropout_p = (float)p; a.dropout_scale = (float)(1.0 / (1.0 - p));
+  a.dropout_thr16 = dropout_threshold16(p); a.seed = seed; a.offset = offset; a.mask_bits = mask_bits;
   a.out = y; a.ldo = f_out;
   if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
     ScopedTimer tm("proj_fwd_tcgen05", s);

@@ -2,25 +2,25 @@
 //
 //   out[M,N] = epi( [A1 | A2][M,K] @ B[K,N] )      fp32 in, fp32 out
 //
-// fp32 parity mode ("3xTF32"): every fp32 operand is split as v = hi + lo with
-// hi = v with the low 13 mantissa bits cleared (exactly a TF32 number) and lo = v - hi
-// (exact in fp32), and the product is accumulated in fp32 in TMEM as
-//   A_hi*B_hi + A_lo*B_hi + A_hi*B_lo            (the dropped lo*lo term is < 2^-22 relative)
-// which keeps the normalised error of the projection at the 1e-6 level (1e-5 bar).
+// fp32 parity mode ("3xTF32"): every fp32 operand is split as v = hi + lo with hi = v rounded to
+// the nearest TF32 number and lo = v - hi (exact in fp32), and the product is accumulated in fp32
+// in TMEM as  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (the dropped lo*lo term is < 2^-24 relative),
+// which keeps the normalised error of the projection at the 1e-6 level (bar: 1e-5).
 //
 // Design (one persistent CTA per SM, no cluster):
-//  * a CTA owns ONE column slice of BN outputs (BN*K*8 bytes of B, hi+lo, stay resident in
-//    shared memory for the whole kernel) and walks 128-row tiles; the CTAs that own the other
-//    slices of the same row tile run next to it, so the second read of the A tile hits L2.
-//  * 16 producer warps stream A: 128-bit global loads issued 4 K-chunks ahead (register
-//    prefetch hides HBM latency), hi/lo split, conflict-free stores into a 2-stage ring of
-//    K-major no-swizzle UMMA tiles; generic->async proxy fence; mbarrier arrive.
-//  * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) -- 3 MMAs per
-//    K-step -- into one of two TMEM accumulators and tcgen05.commit's the stage/accumulator
-//    barriers.
-//  * 4 epilogue warps tcgen05.ld their 32 TMEM lanes, apply bias / degree normalisation /
-//    relu / dropout in registers, transpose through a padded shared staging tile and write
-//    128-byte row segments.
+//  * a CTA owns ONE column slice of BN outputs (BN*K*8 bytes of B, hi+lo, resident in shared
+//    memory for the whole kernel) and walks 128-row tiles; the CTAs owning the other slices of a
+//    row tile run next to it, so the second read of the A tile is an L2 hit.
+//  * 16 producer warps stream A: 128-bit global loads issued 4 K-chunks ahead (register prefetch
+//    hides HBM latency), hi/lo split, conflict-free stores into a 2-stage ring of K-major
+//    no-swizzle UMMA tiles; generic->async proxy fence; one mbarrier arrive per warp.
+//  * one warp issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step) from an
+//    elected lane into one of two TMEM accumulators and tcgen05.commit's the barriers.
+//  * 8 epilogue warps (two per TMEM lane quarter, each owning alternate 32-column chunks)
+//    tcgen05.ld the accumulator, apply bias / degree normalisation / relu / dropout in
+//    registers, transpose through a padded shared staging tile and write 64-byte row segments.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mpgnn {
@@ -31,13 +31,17 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                       // fp32 elements per pipeline stage (4 MMA K-steps)
 constexpr int kStages = 2;
 constexpr int kPrefetch = 4;                      // chunks in flight in producer registers
-constexpr int kEpiWarps = 4;
 constexpr int kProducerWarps = 16;
-constexpr int kThreads = (kEpiWarps + 1 + kProducerWarps) * 32;   // 672
+constexpr int kEpiWarps = 8;
+// Warp roles by warp id: producers first, epilogue warps next (id % 4 = TMEM lane quarter;
+// kProducerWarps is a multiple of 4), the single MMA-issuing warp last.
+constexpr int kMmaWarp = kProducerWarps + kEpiWarps;              // 24
+constexpr int kThreads = (kMmaWarp + 1) * 32;                     // 800
 constexpr int kProducerThreads = kProducerWarps * 32;             // 512
 constexpr int kStageBytes = kTileM * kChunkK * 4;                 // 16 KB per hi or lo
-constexpr int kEpiCols = 32;
-constexpr int kEpiLd = kEpiCols + 4;                              // padded staging row (floats)
+constexpr int kEpiCols = 32;                                      // columns per tcgen05.ld
+constexpr int kStgCols = 16;                                      // columns per staging pass
+constexpr int kStgLd = kStgCols + 4;                              // padded staging row (floats)
 constexpr int kMaxBBytes = 131072;                                // hi + lo of the resident slice
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -64,6 +68,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -79,15 +94,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes; `lbo` = byte distance between
-// the two K-adjacent core matrices of one MMA, `sbo` = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;  // descriptor version (Blackwell)
-  return d;         // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+// core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes; LBO = byte distance between
+// the two K-adjacent core matrices of one MMA (128 here), SBO = byte distance between 8-row
+// groups.  bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
+// [61,64) layout type 0 (SWIZZLE_NONE).  The low word is advanced with plain adds.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (8u << 16); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t lo, uint32_t sbo) {
+  return (uint64_t)lo | ((uint64_t)(((sbo >> 4) & 0x3FFFu) | (1u << 14)) << 32);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, tf32 x tf32, both K-major
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
@@ -106,8 +119,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// hi = v rounded to nearest TF32 (low 13 mantissa bits zero afterwards), so |v - hi| <= 2^-12 |v| with a
-// random sign: the dropped lo*lo term stays below 2^-24 relative and does not accumulate a bias.
+// hi = v rounded to nearest TF32 (low 13 mantissa bits zero afterwards): |v - hi| <= 2^-12 |v|
 __device__ __forceinline__ float tf32_hi(float v) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -122,7 +134,8 @@ struct Params {
   const float* bias;
   int relu;
   const int32_t* deg_ptr; int deg_cols;
-  int dropout_mode; float dropout_p; float dropout_scale; uint64_t seed; uint64_t offset; const uint8_t* mask_bits;
+  int dropout_mode; uint32_t dropout_thr16; float dropout_scale; uint64_t seed; uint64_t offset;
+  const uint8_t* mask_bits;
   float* out; int64_t ldo;
 };
 
@@ -150,8 +163,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   uint8_t* sm_b_hi = smem;
   uint8_t* sm_b_lo = smem + b_bytes;
   uint8_t* sm_a = smem + 2 * b_bytes;                     // kStages x {hi, lo}
-  float* sm_epi = reinterpret_cast<float*>(sm_a + kStages * 2 * kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm_epi) + kEpiWarps * 32 * kEpiLd * 4);
+  float* sm_stg = reinterpret_cast<float*>(sm_a + kStages * 2 * kStageBytes);   // kEpiWarps x 32 x kStgLd
+  float* sm_bias = sm_stg + kEpiWarps * 32 * kStgLd;                            // BN floats (slice bias)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_bias + 128);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   const int group = blockIdx.x / p.n_slices;
   const int n_groups = gridDim.x / p.n_slices;
   const int64_t n_tiles = (p.m + kTileM - 1) / kTileM;
-  const int64_t my_tiles = (group < n_tiles) ? (n_tiles - group + n_groups - 1) / n_groups : 0;
+  const int my_tiles = (group < n_tiles) ? (int)((n_tiles - group + n_groups - 1) / n_groups) : 0;
   const int kch = K / kChunkK;
 
   if (tid == 0) {
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kEpiWarps) {  // TMEM: two fp32 accumulators of BN columns
+  if (warp == kMmaWarp) {  // TMEM: two fp32 accumulators of BN columns
     const uint32_t ncols = 2 * BN;
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(ncols)
@@ -190,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     uint4* dst = reinterpret_cast<uint4*>(sm_b_hi);
     const int n16 = 2 * b_bytes / 16;
     for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+    if (tid < BN) sm_bias[tid] = (p.bias != nullptr) ? __ldg(p.bias + slice * BN + tid) : 0.f;
     fence_proxy_async();
   }
   tc_fence_before();
@@ -197,136 +212,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kEpiWarps) {
-    // ================================ epilogue =========================================
-    float* stg = sm_epi + warp * 32 * kEpiLd;
-    const int64_t mask_ld = (p.n + 7) / 8;
-    for (int64_t ti = 0; ti < my_tiles; ++ti) {
-      const int buf = (int)(ti & 1);
-      const uint32_t ph = (uint32_t)((ti >> 1) & 1);
-      const int64_t row0 = (group + ti * n_groups) * (int64_t)kTileM;
-      const int64_t row = row0 + warp * 32 + lane;          // the TMEM lane this thread reads
-      mbar_wait(bar_tfull + 8 * buf, ph);
-      tc_fence_after();
-      float inv_den = 1.f;
-      if (p.deg_ptr != nullptr && row < p.m) {
-        const int d = __ldg(p.deg_ptr + row + 1) - __ldg(p.deg_ptr + row);
-        inv_den = (float)max(d, 1);
-      }
-      for (int cc = 0; cc < BN / kEpiCols; ++cc) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + cc * kEpiCols) + ((uint32_t)(warp * 32) << 16);
-        tmem_ld32(taddr, v);
-        const int col0 = slice * BN + cc * kEpiCols;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float o[4];
-          uint4 rnd = make_uint4(0, 0, 0, 0);
-          if (p.dropout_mode == 1) {
-            const uint64_t blk = ((uint64_t)row * (uint64_t)p.n + (uint64_t)(col0 + 4 * q)) >> 2;
-            rnd = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)p.offset,
-                                           (uint32_t)(p.offset >> 32)),
-                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-          }
-          const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = col0 + 4 * q + j;
-            float x = __uint_as_float(v[4 * q + j]);
-            if (p.bias != nullptr) x += __ldg(p.bias + col);
-            if (col < p.deg_cols) x = x / inv_den;
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (p.dropout_mode == 1) {
-              x = ((float)(rr[j] >> 8) * (1.0f / 16777216.0f) >= p.dropout_p) ? x * p.dropout_scale : 0.f;
-            } else if (p.dropout_mode == 2 && row < p.m) {
-              const uint8_t byte = __ldg(p.mask_bits + row * mask_ld + (col >> 3));
-              x = ((byte >> (7 - (col & 7))) & 1) ? x * p.dropout_scale : 0.f;
-            }
-            o[j] = x;
-          }
-          *reinterpret_cast<float4*>(stg + lane * kEpiLd + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-        __syncwarp();
-        // transposed read: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-#pragma unroll
-        for (int r4 = 0; r4 < 32; r4 += 4) {
-          const int rl = r4 + (lane >> 3);
-          const int64_t grow = row0 + warp * 32 + rl;
-          const float4 val = *reinterpret_cast<const float4*>(stg + rl * kEpiLd + 4 * (lane & 7));
-          if (grow < p.m) *reinterpret_cast<float4*>(p.out + grow * p.ldo + col0 + 4 * (lane & 7)) = val;
-        }
-        __syncwarp();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-    }
-  } else if (warp == kEpiWarps) {
-    // ================================ MMA issuer ========================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(kTileM, BN);
-      const uint32_t a_sbo = (kChunkK / 4) * 128, b_sbo = (uint32_t)(K / 4) * 128;
-      const uint32_t sa = smem_u32(sm_a), sbh = smem_u32(sm_b_hi), sbl = smem_u32(sm_b_lo);
-      int64_t it = 0;
-      for (int64_t ti = 0; ti < my_tiles; ++ti) {
-        const int buf = (int)(ti & 1);
-        const uint32_t ph = (uint32_t)((ti >> 1) & 1);
-        mbar_wait(bar_tempty + 8 * buf, ph ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        for (int c = 0; c < kch; ++c, ++it) {
-          const int s = (int)(it % kStages);
-          const uint32_t sph = (uint32_t)((it / kStages) & 1);
-          mbar_wait(bar_full + 8 * s, sph);
-          tc_fence_after();
-          const uint32_t a_hi = sa + (uint32_t)s * 2 * kStageBytes, a_lo = a_hi + kStageBytes;
-#pragma unroll
-          for (int j = 0; j < kChunkK / 8; ++j) {
-            const uint64_t dah = make_desc(a_hi + j * 256, 128, a_sbo);
-            const uint64_t dal = make_desc(a_lo + j * 256, 128, a_sbo);
-            const uint32_t boff = (uint32_t)(c * (kChunkK / 4) + j * 2) * 128;
-            const uint64_t dbh = make_desc(sbh + boff, 128, b_sbo);
-            const uint64_t dbl = make_desc(sbl + boff, 128, b_sbo);
-            umma_tf32(d_tmem, dah, dbh, idesc, (c | j) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, dal, dbh, idesc, 1u);
-            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
-          }
-          umma_commit(bar_empty + 8 * s);       // stage reusable once these MMAs have read it
-        }
-        umma_commit(bar_tfull + 8 * buf);       // accumulator complete
-      }
-    }
-  } else {
+  if (warp < kProducerWarps) {
     // ================================ A producers =======================================
-    const int pt = tid - (kEpiWarps + 1) * 32;     // 0..511
     // two 16-byte units per thread and chunk; lane -> (row-in-core r, k-core c4) keeps the
     // shared-memory stores conflict free and the global loads sector aligned
-    int u_row[2], u_core[2];
+    int u_row[2], u_koff[2], u_soff[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int idx = pt + kProducerThreads * u;   // 0..1023
+      const int idx = tid + kProducerThreads * u;   // 0..1023
       const int r = idx & 7, c4 = (idx >> 3) & 3, q = idx >> 5;
       u_row[u] = (q & 15) * 8 + r;
-      u_core[u] = (q >> 4) * 4 + c4;
+      const int core = (q >> 4) * 4 + c4;
+      u_koff[u] = core * 4;
+      u_soff[u] = (u_row[u] >> 3) * ((kChunkK / 4) * 128) + core * 128 + (u_row[u] & 7) * 16;
     }
-    const int64_t total = my_tiles * kch;
+    const int total = my_tiles * kch;
     float4 buf[kPrefetch][2];
-    auto issue = [&](int64_t it, float4 (&dst)[2]) {
-      const int64_t ti = it / kch;
-      const int c = (int)(it % kch);
-      const int64_t row0 = (group + ti * n_groups) * (int64_t)kTileM;
-      const int kbase = c * kChunkK;
-      const float* src;
-      int64_t ld;
-      int koff;
-      if (kbase < p.k1) { src = p.a1; ld = p.lda1; koff = kbase; }
-      else { src = p.a2; ld = p.lda2; koff = kbase - p.k1; }
+    // prefetch cursor (tile, chunk) advanced incrementally: no 64-bit div/mod in the loop
+    int pf_tile = 0, pf_c = 0;
+    auto issue = [&](float4 (&dst)[2]) {
+      const int64_t row0 = (int64_t)(group + (int64_t)pf_tile * n_groups) * kTileM;
+      const int kbase = pf_c * kChunkK;
+      const bool first = kbase < p.k1;
+      const float* src = first ? p.a1 : p.a2;
+      const int64_t ld = first ? p.lda1 : p.lda2;
+      const int koff = first ? kbase : kbase - p.k1;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int64_t row = row0 + u_row[u];
-        dst[u] = (row < p.m) ? __ldg(reinterpret_cast<const float4*>(src + row * ld + koff + u_core[u] * 4))
+        dst[u] = (row < p.m) ? __ldg(reinterpret_cast<const float4*>(src + row * ld + koff + u_koff[u]))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (++pf_c == kch) { pf_c = 0; ++pf_tile; }
     };
     auto store = [&](int s, const float4 (&src)[2]) {
       uint8_t* hi_base = sm_a + (size_t)s * 2 * kStageBytes;
@@ -335,35 +252,144 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         const float4 v = src[u];
         const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
         const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        const int off = (u_row[u] >> 3) * ((kChunkK / 4) * 128) + u_core[u] * 128 + (u_row[u] & 7) * 16;
-        *reinterpret_cast<float4*>(hi_base + off) = h;
-        *reinterpret_cast<float4*>(hi_base + kStageBytes + off) = l;
+        *reinterpret_cast<float4*>(hi_base + u_soff[u]) = h;
+        *reinterpret_cast<float4*>(hi_base + kStageBytes + u_soff[u]) = l;
       }
     };
 #pragma unroll
     for (int j = 0; j < kPrefetch; ++j)
-      if (j < total) issue(j, buf[j]);
-    for (int64_t it0 = 0; it0 < total; it0 += kPrefetch) {
+      if (j < total) issue(buf[j]);
+    int s = 0;
+    uint32_t sph = 0;      // parity of the current use of stage s
+    for (int it0 = 0; it0 < total; it0 += kPrefetch) {
 #pragma unroll
       for (int j = 0; j < kPrefetch; ++j) {
-        const int64_t it = it0 + j;
+        const int it = it0 + j;
         if (it < total) {
-          const int s = (int)(it % kStages);
-          const uint32_t sph = (uint32_t)((it / kStages) & 1);
           mbar_wait(bar_empty + 8 * s, sph ^ 1u);
           store(s, buf[j]);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full + 8 * s);
-          if (it + kPrefetch < total) issue(it + kPrefetch, buf[j]);
+          if (it + kPrefetch < total) issue(buf[j]);
+          if (++s == kStages) { s = 0; sph ^= 1u; }
         }
+      }
+    }
+  } else if (warp < kMmaWarp) {
+    // ================================ epilogue =========================================
+    const int ew = warp - kProducerWarps;        // 0..7
+    const int quarter = ew & 3;                  // == warp % 4: the TMEM lanes this warp may read
+    const int half = ew >> 2;                    // owns 32-column chunks cc = half, half+2, ...
+    float* stg = sm_stg + ew * 32 * kStgLd;
+    const int64_t mask_ld = (p.n + 7) / 8;
+    const bool do_drop_seed = p.dropout_mode == 1, do_drop_mask = p.dropout_mode == 2;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int buf = ti & 1;
+      const uint32_t ph = (uint32_t)((ti >> 1) & 1);
+      const int64_t row0 = (int64_t)(group + (int64_t)ti * n_groups) * kTileM;
+      const int64_t row = row0 + quarter * 32 + lane;       // the TMEM lane this thread reads
+      float inv_deg = 1.f;
+      if (p.deg_ptr != nullptr && row < p.m) {
+        const int d = __ldg(p.deg_ptr + row + 1) - __ldg(p.deg_ptr + row);
+        inv_deg = 1.0f / (float)max(d, 1);
+      }
+      mbar_wait(bar_tfull + 8 * buf, ph);
+      tc_fence_after();
+      for (int cc = half; cc < BN / kEpiCols; cc += 2) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + cc * kEpiCols) + ((uint32_t)(quarter * 32) << 16);
+        tmem_ld32(taddr, v);
+        const int lcol0 = cc * kEpiCols;                    // column inside the slice
+        const int col0 = slice * BN + lcol0;                // global output column
+        const bool scale_deg = col0 < p.deg_cols;           // deg_cols is a multiple of 32 (checked on host)
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {                    // two staging passes of 16 columns
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int e0 = hp * 16 + 4 * q;                 // first of 4 consecutive elements
+            uint64_t rnd = 0;
+            if (do_drop_seed)
+              rnd = dropout_word(p.seed, p.offset, ((uint64_t)row * (uint64_t)p.n + (uint64_t)(col0 + e0)) >> 2);
+            uint32_t mbits = 0;
+            if (do_drop_mask && row < p.m) {
+              const int c = col0 + e0;                      // multiple of 4: the nibble of one byte
+              const uint32_t byte = __ldg(p.mask_bits + row * mask_ld + (c >> 3));
+              mbits = (c & 4) ? (byte & 0xFu) : (byte >> 4);   // MSB-first: bit 3 = first element
+            }
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x = __uint_as_float(v[e0 + j]) + sm_bias[lcol0 + e0 + j];
+              if (scale_deg) x *= inv_deg;
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (do_drop_seed)
+                x = ((uint32_t)(rnd >> (16 * j)) & 0xFFFFu) >= p.dropout_thr16 ? x * p.dropout_scale : 0.f;
+              else if (do_drop_mask)
+                x = ((mbits >> (3 - j)) & 1u) ? x * p.dropout_scale : 0.f;
+              o[j] = x;
+            }
+            *reinterpret_cast<float4*>(stg + lane * kStgLd + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          __syncwarp();
+          // transposed read: 4 lanes cover one 64-byte row segment; a quarter-warp reads rows
+          // {j, j+4} so that its 8 lanes hit 8 distinct bank groups (row stride 20 floats)
+#pragma unroll
+          for (int r8 = 0; r8 < 32; r8 += 8) {
+            const int rl = r8 + ((lane >> 3) & 3) + 4 * ((lane >> 2) & 1);
+            const int64_t grow = row0 + quarter * 32 + rl;
+            const float4 val = *reinterpret_cast<const float4*>(stg + rl * kStgLd + 4 * (lane & 3));
+            if (grow < p.m)
+              *reinterpret_cast<float4*>(p.out + grow * p.ldo + col0 + hp * 16 + 4 * (lane & 3)) = val;
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+  } else {
+    // ================================ MMA issuer (whole warp converged; one elected lane issues) ====
+    const uint32_t idesc = make_idesc(kTileM, BN);
+    const uint32_t a_sbo = (kChunkK / 4) * 128, b_sbo = (uint32_t)(K / 4) * 128;
+    const uint32_t a_lo0 = desc_lo(smem_u32(sm_a));
+    const uint32_t bh_lo0 = desc_lo(smem_u32(sm_b_hi)), bl_lo0 = desc_lo(smem_u32(sm_b_lo));
+    int s = 0;
+    uint32_t sph = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int buf = ti & 1;
+      const uint32_t ph = (uint32_t)((ti >> 1) & 1);
+      mbar_wait(bar_tempty + 8 * buf, ph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+      for (int c = 0; c < kch; ++c) {
+        mbar_wait(bar_full + 8 * s, sph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t ah = a_lo0 + (uint32_t)(s * 2 * kStageBytes >> 4), al = ah + (kStageBytes >> 4);
+          const uint32_t boff = (uint32_t)(c * (kChunkK / 4) * 128) >> 4;
+#pragma unroll
+          for (int j = 0; j < kChunkK / 8; ++j) {
+            const uint64_t dah = desc_make(ah + j * 16, a_sbo), dal = desc_make(al + j * 16, a_sbo);
+            const uint64_t dbh = desc_make(bh_lo0 + boff + j * 16, b_sbo);
+            const uint64_t dbl = desc_make(bl_lo0 + boff + j * 16, b_sbo);
+            umma_tf32(d_tmem, dah, dbh, idesc, (c | j) != 0 ? 1u : 0u);
+            umma_tf32(d_tmem, dal, dbh, idesc, 1u);
+            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * s);       // stage reusable once these MMAs have read it
+          if (c == kch - 1) umma_commit(bar_tfull + 8 * buf);   // accumulator complete
+        }
+        __syncwarp();
+        if (++s == kStages) { s = 0; sph ^= 1u; }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kEpiWarps) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     const uint32_t ncols = 2 * BN;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
@@ -381,7 +407,7 @@ static int pick_bn(int64_t k, int64_t n) {
 int proj_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags) {
   if (!(flags & MPGNN_F_TF32X3)) return 0;   // the bf16 mode is not built yet
   const int64_t k = k1 + k2;
-  if (m < 1 || k < tc::kChunkK || k > 256) return 0;
+  if (m < 1 || m >= (1LL << 37) || k < tc::kChunkK || k > 256) return 0;
   if (k1 % tc::kChunkK != 0 || k2 % tc::kChunkK != 0) return 0;
   if (n % 64 != 0 || n > 65536) return 0;
   return pick_bn(k, n) != 0;
@@ -393,6 +419,8 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   const int64_t k = a.k1 + a.k2;
   MPGNN_REQUIRE(proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags), MPGNN_ENOTSUP, "proj_tcgen05: unsupported shape");
   MPGNN_REQUIRE(a.gate == nullptr, MPGNN_ENOTSUP, "proj_tcgen05: gate epilogue not supported");
+  MPGNN_REQUIRE(a.deg_ptr == nullptr || a.deg_cols % tc::kEpiCols == 0, MPGNN_ENOTSUP,
+                "proj_tcgen05: deg_cols must be a multiple of 32");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   MPGNN_REQUIRE(al16(a.a1) && (a.k2 == 0 || al16(a.a2)) && al16(a.out) && a.lda1 % 4 == 0 &&
                     (a.k2 == 0 || a.lda2 % 4 == 0) && a.ldo % 4 == 0,
@@ -407,15 +435,15 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   p.b_img = b_img;
   p.m = a.m; p.n = (int)a.n; p.bn = bn; p.n_slices = n_slices;
   p.bias = a.bias; p.relu = a.relu;
-  p.deg_ptr = a.deg_ptr; p.deg_cols = (int)a.deg_cols;
-  p.dropout_mode = a.dropout_mode; p.dropout_p = a.dropout_p; p.dropout_scale = a.dropout_scale;
+  p.deg_ptr = a.deg_ptr; p.deg_cols = a.deg_ptr ? (int)a.deg_cols : 0;
+  p.dropout_mode = a.dropout_mode; p.dropout_thr16 = a.dropout_thr16; p.dropout_scale = a.dropout_scale;
   p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits;
   p.out = a.out; p.ldo = a.ldo;
   const int64_t n_tiles = ceil_div(a.m, tc::kTileM);
   int64_t grid = n_tiles * n_slices;
   if (grid > kNumSMs) grid = (kNumSMs / n_slices) * n_slices;
   const size_t smem = (size_t)2 * k * bn * 4 + (size_t)tc::kStages * 2 * tc::kStageBytes +
-                      (size_t)tc::kEpiWarps * 32 * tc::kEpiLd * 4 + (2 * tc::kStages + 4) * 8 + 16;
+                      (size_t)tc::kEpiWarps * 32 * tc::kStgLd * 4 + 128 * 4 + (2 * tc::kStages + 4) * 8 + 16;
   MPGNN_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc::gemm_rows_tc_kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p);
   MPGNN_LAUNCH_CHECK();
