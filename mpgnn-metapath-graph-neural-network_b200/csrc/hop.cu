@@ -8,6 +8,15 @@ namespace mpgnn {
 int proj_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags);
 int64_t proj_tcgen05_workspace_floats(int64_t k, int64_t n);
 int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, cudaStream_t s);
+int wgrad_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags);
+int64_t wgrad_tcgen05_workspace_floats(int64_t m, int64_t n);
+int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s);
+
+static int64_t wgrad_ws_floats(int64_t n, int64_t f_in, int64_t f_out) {
+  int64_t a = gemm_tn_partial_floats(n, 2 * f_in + 1, f_out);
+  int64_t b = wgrad_tcgen05_supported(n, f_in, f_in, f_out, MPGNN_F_TF32X3) ? wgrad_tcgen05_workspace_floats(n, f_out) : 0;
+  return a > b ? a : b;
+}
 
 // packed [W;root] followed by its hi/lo UMMA images for the tensor-core path
 static int64_t fwd_ws_floats(int64_t f_in, int64_t f_out) {
@@ -18,7 +27,7 @@ int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
   int64_t floats = 0;
   floats += fwd_ws_floats(f_in, f_out);                                // packed [W;root]
   floats += align_up(n * f_out, 64);                                   // g_z
-  floats += align_up(gemm_tn_partial_floats(n, 2 * f_in + 1, f_out), 64);  // split-K partials
+  floats += align_up(wgrad_ws_floats(n, f_in, f_out), 64);             // split-K partials (SIMT or tcgen05)
   floats += align_up(f_out * 2 * f_in, 64);                            // packed [W^T | root^T]
   floats += align_up(proj_tcgen05_workspace_floats(f_out, 2 * f_in), 64);  // its hi/lo UMMA images
   floats += align_up(n * 2 * f_in, 64);                                // [t | g_z root^T]
@@ -80,7 +89,7 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   (void)ws.take<float>(fwd_ws_floats(f_in, f_out));
   float* gz = ws.take<float>(align_up(n * f_out, 64));
   const int64_t part_floats = gemm_tn_partial_floats(n, 2 * f_in + 1, f_out);
-  float* partials = ws.take<float>(align_up(part_floats, 64));
+  float* partials = ws.take<float>(align_up(wgrad_ws_floats(n, f_in, f_out), 64));
   float* bp2 = ws.take<float>(align_up(f_out * 2 * f_in, 64));
   float* bp2_img = ws.take<float>(align_up(proj_tcgen05_workspace_floats(f_out, 2 * f_in), 64));
   float* t = need_gx ? ws.take<float>(align_up(n * 2 * f_in, 64)) : nullptr;
@@ -102,7 +111,10 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   tn.out2 = groot; tn.ldo2 = f_out;
   tn.out_ones = gbias;
   tn.partials = partials; tn.partial_capacity_floats = part_floats;
-  {
+  if (wgrad_tcgen05_supported(n, f_in, f_in, f_out, flags)) {
+    ScopedTimer tm("wgrad_tn_tcgen05", s);
+    MPGNN_PROPAGATE(launch_wgrad_tcgen05(tn, partials, s));
+  } else {
     ScopedTimer tm("wgrad_tn_simt", s);
     MPGNN_PROPAGATE(launch_gemm_tn(tn, s));
   }

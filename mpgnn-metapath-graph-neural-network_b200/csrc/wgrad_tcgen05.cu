@@ -1,0 +1,337 @@
+// K4 -- weight gradients on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   out1[128,N] = A1[M,128]^T @ B[M,N]     (g_W    = h^T g_z)
+//   out2[128,N] = A2[M,128]^T @ B[M,N]     (g_root = x^T g_z)
+//   colsum[N]   = sum_rows B               (g_bias)
+//
+// The reduction runs over the M node rows, so the node dimension is the MMA K dimension and
+// both operands are "MN-major" as they sit in HBM (features contiguous).  Same 3xTF32 split as
+// the projection kernel (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulate in TMEM).
+//
+// One persistent CTA per SM owns a contiguous range of rows (a fixed function of M, so the
+// summation tree is the same on every run and GPU count) and keeps BOTH 128xN accumulators in
+// TMEM for its whole range; at the end it writes one partial per CTA and a second kernel adds
+// the partials in CTA order (deterministic split-K).
+//  * 16 producer warps stream 32-row chunks of A1, A2 and B: 128-bit loads issued 2 chunks
+//    ahead (one fully coalesced 512-byte node row per warp instruction), hi/lo split, conflict-free
+//    stores into a 2-stage ring of MN-major UMMA tiles in the SWIZZLE_128B_BASE32B layout -- the only
+//    shared-memory layout the hardware accepts for MN-major tf32 operands; they also keep the
+//    running column sums of B in registers.
+//  * one warp issues the 24 MMAs of a chunk (4 K-steps x 2 accumulators x 3 terms).
+#include "tc_common.cuh"
+
+namespace mpgnn {
+
+namespace tcw {
+
+using namespace tc;
+
+constexpr int kRowsPerChunk = 32;                 // node rows (MMA K) per pipeline stage
+constexpr int kFeat = 128;                        // feature width of A1 / A2 (MMA M)
+constexpr int kStagesW = 2;
+constexpr int kProducerWarpsW = 16;
+constexpr int kEpiWarpsW = 4;
+constexpr int kMmaWarpW = kProducerWarpsW + kEpiWarpsW;           // 20
+constexpr int kThreadsW = (kMmaWarpW + 1) * 32;                   // 672
+constexpr int kProducerThreadsW = kProducerWarpsW * 32;
+constexpr int kATileBytes = kRowsPerChunk * kFeat * 4;            // 16 KB (one of hi / lo)
+
+struct ParamsW {
+  const float* a1; int64_t lda1;
+  const float* a2; int64_t lda2;
+  const float* b; int64_t ldb; int n;
+  int64_t m; int64_t rows_per_cta;
+  float* partials;       // [grid][2][128][n]
+  float* colsum_part;    // [grid][32][n]
+};
+
+// instruction descriptor: fp32 accumulate, tf32 x tf32, A and B both MN-major
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+// MN-major tf32 operand tile, SWIZZLE_128B_BASE32B (cute::UMMA::Layout_MN_SW128_32B_Atom):
+// atom = 4 K-rows x 32 MN-elements (4 x 128 bytes); inside a row the four 32-byte chunks are
+// XOR-swizzled with the K-row index (Swizzle<2,5,2> on the byte address).  Element (mn, k) of a
+// tile with `atoms` = width/32 MN-atoms lives at byte
+//   (k/4)*atoms*512 + (mn/32)*512 + (k%4)*128 + ((((mn%32)/8) ^ (k%4))*32) + (mn%8)*4.
+// Descriptor: LBO = 512 (next MN atom), SBO = atoms*512 (next group of 4 K-rows), layout type 1.
+__device__ __forceinline__ uint32_t mn_tile_offset16(int i16, int k, int atoms) {   // i16 = 16-byte unit in the row
+  return (uint32_t)((k >> 2) * atoms * 512 + (i16 >> 3) * 512 + (k & 3) * 128 + ((((i16 & 7) >> 1) ^ (k & 3)) << 5) +
+                    (i16 & 1) * 16);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((512u >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;   // descriptor version
+  d |= 1ull << 61;   // layout type SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int N = p.n;
+  const int b_tile_bytes = kRowsPerChunk * N * 4;                    // one of hi / lo
+  const int stage_bytes = 4 * kATileBytes + 2 * b_tile_bytes;        // a1 hi/lo, a2 hi/lo, b hi/lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * stage_bytes);
+  // bars: full[kStagesW], empty[kStagesW], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesW + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStagesW);
+  const uint32_t bar_done = smem_u32(bars + 2 * kStagesW);
+
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+  int64_t r_end = r_begin + p.rows_per_cta;
+  if (r_end > p.m) r_end = p.m;
+  const int n_chunks = r_begin < r_end ? (int)((r_end - r_begin + kRowsPerChunk - 1) / kRowsPerChunk) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStagesW; ++s) {
+      mbar_init(bar_full + 8 * s, kProducerWarpsW);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarpW) {  // TMEM: D1 and D2, N fp32 columns each
+    const uint32_t ncols = 2 * N;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kProducerWarpsW) {
+    // ================================ producers ==========================================
+    // a warp instruction moves whole node rows: 32 lanes x 16 bytes = one 512-byte row (N = 128) or two
+    // 256-byte rows (N = 64): fully coalesced loads; the swizzled destination keeps each quarter-warp
+    // inside one 128-byte line, so the stores are conflict free.
+    const int n_units_b = kRowsPerChunk * N / 4 / kProducerThreadsW;   // 2 (N=128) or 1 (N=64)
+    const int b_atoms = N / 32;
+    int a_row[2], a_col[2], a_soff[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      a_row[u] = warp * 2 + u;
+      a_col[u] = lane * 4;
+      a_soff[u] = (int)mn_tile_offset16(lane, a_row[u], kFeat / 32);
+    }
+    int b_row[2], b_col[2], b_soff[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (N == 128) {
+        b_row[u] = warp * 2 + u;
+        b_col[u] = lane * 4;
+        b_soff[u] = (int)mn_tile_offset16(lane, b_row[u], b_atoms);
+      } else {                                          // N == 64: one instruction, two rows per warp
+        b_row[u] = warp * 2 + (lane >> 4);
+        b_col[u] = (lane & 15) * 4;
+        b_soff[u] = (int)mn_tile_offset16(lane & 15, b_row[u], b_atoms);
+      }
+    }
+    float4 csum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    float4 buf[2][6];
+    int pf = 0;                                            // next chunk to prefetch
+    auto issue = [&](float4 (&dst)[6]) {
+      const int64_t row0 = r_begin + (int64_t)pf * kRowsPerChunk;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t ra = row0 + a_row[u];
+        const bool ok = ra < r_end;
+        dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a1 + ra * p.lda1 + a_col[u])) : z;
+        dst[2 + u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
+        const int64_t rb = row0 + b_row[u];
+        dst[4 + u] = (u < n_units_b && rb < r_end) ? __ldg(reinterpret_cast<const float4*>(p.b + rb * p.ldb + b_col[u])) : z;
+      }
+      ++pf;
+    };
+    auto split_store = [&](uint8_t* hi_ptr, int lo_delta, const float4& v) {
+      const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      *reinterpret_cast<float4*>(hi_ptr) = h;
+      *reinterpret_cast<float4*>(hi_ptr + lo_delta) = l;
+    };
+    auto store = [&](int s, const float4 (&src)[6]) {
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        split_store(st + a_soff[u], kATileBytes, src[u]);                         // a1: hi @0, lo @16K
+        split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
+        if (u < n_units_b) {
+          split_store(st + 4 * kATileBytes + b_soff[u], b_tile_bytes, src[4 + u]);  // b: hi, lo
+          csum[u].x += src[4 + u].x; csum[u].y += src[4 + u].y; csum[u].z += src[4 + u].z; csum[u].w += src[4 + u].w;
+        }
+      }
+    };
+    if (0 < n_chunks) issue(buf[0]);
+    if (1 < n_chunks) issue(buf[1]);
+    int s = 0;
+    uint32_t sph = 0;
+    for (int it0 = 0; it0 < n_chunks; it0 += 2) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int it = it0 + j;
+        if (it < n_chunks) {
+          mbar_wait(bar_empty + 8 * s, sph ^ 1u);
+          store(s, buf[j]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * s);
+          if (it + 2 < n_chunks) issue(buf[j]);
+          if (++s == kStagesW) { s = 0; sph ^= 1u; }
+        }
+      }
+    }
+    // per-thread column sums of B: a [32][N] slab per CTA, reduced in a fixed order afterwards
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (u < n_units_b)
+        *reinterpret_cast<float4*>(p.colsum_part + ((int64_t)blockIdx.x * kRowsPerChunk + b_row[u]) * N + b_col[u]) = csum[u];
+  } else if (warp == kMmaWarpW) {
+    // ================================ MMA issuer ==========================================
+    const uint32_t idesc = make_idesc_mn(kFeat, N);
+    const uint32_t a_sbo = (kFeat / 32) * 512, b_sbo = (uint32_t)(N / 32) * 512;   // next group of 4 K-rows
+    const uint32_t s0 = smem_u32(smem);
+    int s = 0;
+    uint32_t sph = 0;
+    for (int it = 0; it < n_chunks; ++it) {
+      mbar_wait(bar_full + 8 * s, sph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = s0 + (uint32_t)(s * stage_bytes);
+#pragma unroll
+        for (int kg = 0; kg < kRowsPerChunk / 8; ++kg) {
+          // one MMA consumes K = 8 node rows = two groups of 4 K-rows
+          const uint32_t ao = kg * 2 * a_sbo, bo = kg * 2 * b_sbo;
+          const uint64_t a1h = desc_mn(st + ao, a_sbo), a1l = desc_mn(st + kATileBytes + ao, a_sbo);
+          const uint64_t a2h = desc_mn(st + 2 * kATileBytes + ao, a_sbo);
+          const uint64_t a2l = desc_mn(st + 3 * kATileBytes + ao, a_sbo);
+          const uint64_t bh = desc_mn(st + 4 * kATileBytes + bo, b_sbo);
+          const uint64_t bl = desc_mn(st + 4 * kATileBytes + b_tile_bytes + bo, b_sbo);
+          const uint32_t acc = (it | kg) != 0 ? 1u : 0u;
+          umma_tf32(tmem_base, a1h, bh, idesc, acc);
+          umma_tf32(tmem_base, a1l, bh, idesc, 1u);
+          umma_tf32(tmem_base, a1h, bl, idesc, 1u);
+          umma_tf32(tmem_base + (uint32_t)N, a2h, bh, idesc, acc);
+          umma_tf32(tmem_base + (uint32_t)N, a2l, bh, idesc, 1u);
+          umma_tf32(tmem_base + (uint32_t)N, a2h, bl, idesc, 1u);
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (it == n_chunks - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+      if (++s == kStagesW) { s = 0; sph ^= 1u; }
+    }
+  } else {
+    // ================================ final epilogue: TMEM -> per-CTA partial =============
+    const int ew = warp - kProducerWarpsW;          // == warp % 4: TMEM lane quarter
+    float* part = p.partials + (int64_t)blockIdx.x * 2 * kFeat * N;
+    const int mrow = ew * 32 + lane;                // feature row of A1 / A2
+    if (n_chunks > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+    }
+    for (int d = 0; d < 2; ++d) {
+      for (int cc = 0; cc < N / 32; ++cc) {
+        uint32_t v[32];
+        if (n_chunks > 0) {
+          tmem_ld32(tmem_base + (uint32_t)(d * N + cc * 32) + ((uint32_t)(ew * 32) << 16), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        float* dst = part + ((int64_t)d * kFeat + mrow) * N + cc * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(dst + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarpW) {
+    tc_fence_after();
+    const uint32_t ncols = 2 * N;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+// fixed-order reduction of the per-CTA partials (and of the [grid][32][N] column-sum slabs)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ colsum_part,
+                                    int grid, int n, float* __restrict__ out1, int64_t ldo1,
+                                    float* __restrict__ out2, int64_t ldo2, float* __restrict__ colsum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 2 * kFeat * n;
+  if (i < per) {
+    float s = 0.f;
+    for (int c = 0; c < grid; ++c) s += partials[(int64_t)c * per + i];
+    const int d = i / (kFeat * n), r = (i / n) % kFeat, col = i % n;
+    if (d == 0) out1[(int64_t)r * ldo1 + col] = s;
+    else out2[(int64_t)r * ldo2 + col] = s;
+  } else if (i < per + n && colsum != nullptr) {
+    const int col = i - per;
+    float s = 0.f;
+    for (int c = 0; c < grid; ++c)
+      for (int r = 0; r < kRowsPerChunk; ++r) s += colsum_part[((int64_t)c * kRowsPerChunk + r) * n + col];
+    colsum[col] = s;
+  }
+}
+
+}  // namespace tcw
+
+int wgrad_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags) {
+  if (!(flags & MPGNN_F_TF32X3)) return 0;
+  return m >= 1 && k1 == tcw::kFeat && k2 == tcw::kFeat && (n == 64 || n == 128);
+}
+
+static void wgrad_split(int64_t m, int* grid, int64_t* rows_per_cta) {
+  int64_t rpc = align_up(ceil_div(m, kNumSMs), tcw::kRowsPerChunk);
+  int64_t g = ceil_div(m, rpc);
+  *grid = (int)g;
+  *rows_per_cta = rpc;
+}
+
+int64_t wgrad_tcgen05_workspace_floats(int64_t m, int64_t n) {
+  int grid;
+  int64_t rpc;
+  wgrad_split(m, &grid, &rpc);
+  return (int64_t)grid * (2 * tcw::kFeat * n + tcw::kRowsPerChunk * n);
+}
+
+int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
+  MPGNN_REQUIRE(wgrad_tcgen05_supported(a.m, a.k1, a.k2, a.n, MPGNN_F_TF32X3), MPGNN_ENOTSUP,
+                "wgrad_tcgen05: unsupported shape");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  MPGNN_REQUIRE(al16(a.a1) && al16(a.a2) && al16(a.b) && a.lda1 % 4 == 0 && a.lda2 % 4 == 0 && a.ldb % 4 == 0,
+                MPGNN_EINVAL, "wgrad_tcgen05: operands must be 16-byte aligned with strides multiple of 4");
+  int grid;
+  int64_t rpc;
+  wgrad_split(a.m, &grid, &rpc);
+  tcw::ParamsW p{};
+  p.a1 = a.a1; p.lda1 = a.lda1;
+  p.a2 = a.a2; p.lda2 = a.lda2;
+  p.b = a.b; p.ldb = a.ldb; p.n = (int)a.n;
+  p.m = a.m; p.rows_per_cta = rpc;
+  p.partials = ws;
+  p.colsum_part = ws + (int64_t)grid * 2 * tcw::kFeat * a.n;
+  const size_t smem = (size_t)tcw::kStagesW * (4 * tcw::kATileBytes + 2 * tcw::kRowsPerChunk * a.n * 4) +
+                      (2 * tcw::kStagesW + 1) * 8 + 16;
+  MPGNN_CUDA_CHECK(cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tcw::wgrad_tc_kernel<<<grid, tcw::kThreadsW, smem, s>>>(p);
+  MPGNN_LAUNCH_CHECK();
+  const int total = 2 * tcw::kFeat * (int)a.n + (int)a.n;
+  tcw::wgrad_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(p.partials, p.colsum_part, grid, (int)a.n,
+                                                                          a.out1, a.ldo1, a.out2, a.ldo2, a.out_ones);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+}  // namespace mpgnn
