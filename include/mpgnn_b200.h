@@ -141,6 +141,22 @@ int mpgnn_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float
                     int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                     void* stream);
 
+/* ---- K5: search-stage relation scorer, non-bag mode ------------------------------------
+ * score_relation_parallel (main.py:727-760) = `epochs` x train() (main.py:641-673) of the Score
+ * net (model.py:26-125): pred[src] = max over the relation's destinations of w[dst] (first
+ * maximum in edge order), MSE(mean) against d_labels[src] (float 0/1 per node), Adam(lr) on w,
+ * clamp to [0,1].  Sources = nodes with at least one edge of `relation` (first search iteration,
+ * d_source_mask NULL) or the nodes flagged in d_source_mask (uint8 [N]); a flagged node without
+ * such an edge predicts 0 and still counts in the mean, as in the reference (main.py:653-656).
+ * d_w [N] in/out (initial weights: only destination entries matter); d_m, d_v [N] Adam state
+ * (zeroed by the call); d_loss_traj [epochs] receives the loss computed BEFORE each update (the
+ * reference returns the last one); d_argmax_dst int32 [N] receives the destination each source
+ * selected in the last forward (-1 for non-sources).  Deterministic (no float atomics). */
+int64_t mpgnn_score_workspace_bytes(int64_t num_nodes);
+int mpgnn_score_relation(const mpgnn_graph* g, int64_t relation, float* d_w, const float* d_labels,
+                         const uint8_t* d_source_mask, int64_t epochs, double lr, float* d_m, float* d_v, float* d_loss_traj, int32_t* d_argmax_dst,
+                         void* d_workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,12 @@ int launch_macro_f1(const float* logp, int64_t c, const int64_t* idx, const int6
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int64_t step, double lr, double beta1,
                 double beta2, double eps, double wd, cudaStream_t s);
 
+int64_t score_workspace_bytes(int64_t n);
+int score_relation(const mpgnn_graph_impl* g, int64_t rel, float* w, const float* labels, const uint8_t* src_mask,
+                   int64_t epochs, double lr,
+                   float* m, float* v, float* loss_traj, int32_t* argmax_dst, void* ws_ptr, int64_t ws_bytes,
+                   cudaStream_t s);
+
 }  // namespace mpgnn
 
 using namespace mpgnn;
@@ -294,6 +300,15 @@ int mpgnn_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float
                     void* stream) {
   return launch_adam(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, step, lr, beta1, beta2, eps, weight_decay,
                      stream_of(stream));
+}
+
+int64_t mpgnn_score_workspace_bytes(int64_t num_nodes) { return score_workspace_bytes(num_nodes); }
+
+int mpgnn_score_relation(const mpgnn_graph* g, int64_t relation, float* d_w, const float* d_labels,
+                         const uint8_t* d_source_mask, int64_t epochs, double lr, float* d_m, float* d_v, float* d_loss_traj, int32_t* d_argmax_dst,
+                         void* d_workspace, int64_t workspace_bytes, void* stream) {
+  return score_relation(impl(g), relation, d_w, d_labels, d_source_mask, epochs, lr, d_m, d_v, d_loss_traj, d_argmax_dst, d_workspace,
+                        workspace_bytes, stream_of(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,141 @@
+"""CPU tests of the search stage: the oracle against the reference goldens, the host-side
+restatements (dictionaries, relation discovery, selection rules, partitions) and the multi-rank
+fan-out over a world_size-2 gloo group with stand-in scorers."""
+import os
+import random
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden, fixture_as_torch
+from oracle import search_oracle as so
+
+import mpgnn_b200
+from mpgnn_b200 import search
+
+
+def _data(fx):
+    return mpgnn_b200.Data(x=fx["x"], edge_index=fx["edge_index"], edge_type=fx["edge_type"],
+                           labels=fx["labels"].unsqueeze(-1), num_nodes=fx["x"].size(0), source_nodes_mask=[])
+
+
+def test_oracle_scorer_matches_reference_golden(fx3):
+    g = load_golden("search_len3")
+    ei, et, lab = fx3["edge_index"].numpy(), fx3["edge_type"].numpy(), fx3["labels"].numpy()
+    rels = so.connected_relations_step0(ei, et, lab)
+    assert rels == g["actual_relations"].tolist()
+    losses = []
+    for r in rels:
+        traj, w, arg, keys = so.score_relation(ei, et, r, lab, fx3["x"].size(0))
+        assert keys == g["r%d_dest_keys" % r].tolist()                  # dict order drives the RNG stream
+        ref = g["r%d_loss_traj" % r]
+        assert np.allclose(traj, ref, rtol=1e-5, atol=1e-9)
+        assert arg == g["r%d_argmax_dst" % r].tolist()
+        assert np.allclose(w[torch.tensor(keys)].numpy(), g["r%d_final_w" % r], atol=1e-6)
+        losses.append(traj[-1])
+    assert so.gap_select_step0(rels, losses) == g["step0_best"].tolist()
+
+
+def test_host_dictionaries_and_relations_match_oracle(fx3):
+    g = load_golden("search_len3")
+    data = _data(fx3)
+    rels = search.node_types_and_connected_relations(data, BAGS=False, dataset="synthetic")
+    assert rels == g["actual_relations"].tolist()
+    for r in rels:
+        src = np.unique(fx3["edge_index"].numpy()[0][fx3["edge_type"].numpy() == r]).tolist()
+        ed, dd = search.create_edge_dictionary(data, r, src, BAGS=False, dataset="synthetic")
+        ed_o, dd_o = so.relation_dictionaries(fx3["edge_index"].numpy(), fx3["edge_type"].numpy(), r,
+                                              fx3["labels"].numpy())
+        assert list(ed.keys()) == g["r%d_sources" % r].tolist() and ed == ed_o
+        assert list(dd.keys()) == g["r%d_dest_keys" % r].tolist() and dd == dd_o
+        random.seed(search.SCORER_SEED_BASE + r)
+        w = search.initialize_weights(data, dd, BAGS=False)
+        assert np.allclose(w[torch.tensor(list(dd.keys()))].numpy(), g["r%d_init_w" % r], atol=0)
+    with pytest.raises(NotImplementedError):
+        search.node_types_and_connected_relations(data, BAGS=True, dataset="synthetic")
+
+
+def test_selection_rules_and_partitions():
+    # gap rule (main.py:1346-1355): `<=` the value below the largest gap; < 2 gaps keeps everything
+    assert search.gap_select_step0([5, 6, 7, 8], [0.30, 0.01, 0.02, 0.31]) == [6, 7]
+    assert search.gap_select_step0([1, 2], [0.5, 0.1]) == [1, 2]
+    assert search.gap_select_step0([3], [0.2]) == [3]
+    assert search.gap_select_step0([1, 2, 3], [0.1, 0.1, 0.9]) == [1, 2]
+    # np.array_split / block partition semantics of the reference
+    for n in (0, 1, 5, 7, 16):
+        for size in (1, 2, 3, 8):
+            items = list(range(10, 10 + n))
+            parts = [search.relation_split(items, size, r) for r in range(size)]
+            assert sum(parts, []) == items
+            assert parts == [[int(v) for v in a] for a in np.array_split(np.asarray(items), size)]
+            blocks = [search.candidate_block(n, size, r) for r in range(size)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(size - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    # final selection (main.py:1463-1476): stable top-3, greedy union while test F1 strictly improves
+    calls = []
+
+    def union(metas):
+        calls.append([list(m) for m in metas])
+        return {1: 0.8, 2: 0.9, 3: 0.9}[len(metas)]
+
+    fm, f1 = search.final_selection({"[1]": 0.7, "[2, 0]": 0.9, "[3]": 0.9, "[4]": 0.1}, union)
+    assert fm == [[2, 0], [3]] and f1 == 0.9 and calls[0] == [[2, 0]] and len(calls) == 3
+
+
+def _stub_score(data, rel):
+    return {0: 0.0, 1: 0.0196, 2: 0.21, 3: 0.22}.get(int(rel), 0.5)
+
+
+def _stub_eval(meta):
+    return 0.5 + 0.1 * meta[0]
+
+
+def _stub_union(metas):
+    return 0.6 + 0.05 * len(metas) if len(metas) < 2 else 0.6
+
+
+def _worker(rank, size, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(size))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    fx = fixture_as_torch("fixture_len3")
+    fx["edge_type"] = fx["edge_type"].clone()
+    fx["edge_type"][::7] = 3          # make more relations leave positive nodes
+    fx["edge_type"][::11] = 2
+    res = search.greedy_search(_data(fx), None, 2, 64, 4, 64, 2, "synthetic", comm=search.Comm(), score_fn=_stub_score,
+                               eval_fn=_stub_eval, union_fn=_stub_union)
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fanout_world_size_2_gloo_matches_single_process():
+    fx = fixture_as_torch("fixture_len3")
+    fx["edge_type"] = fx["edge_type"].clone()
+    fx["edge_type"][::7] = 3
+    fx["edge_type"][::11] = 2
+    single = search.greedy_search(_data(fx), None, 2, 64, 4, 64, 2, "synthetic", comm=search.Comm(),
+                                  score_fn=_stub_score, eval_fn=_stub_eval, union_fn=_stub_union)
+    assert len(single["relations"]) == 4 and single["kept"] == [r for r in single["relations"] if r in (0, 1)]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(2):           # every rank derives the same decisions as the single-process run
+        assert results[r] == single
