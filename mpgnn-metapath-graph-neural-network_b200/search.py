@@ -113,7 +113,7 @@ def run_scorer(graph, relation, weights, node_labels, source_mask=None, epochs=S
 def score_relation_parallel(data, relation, source_nodes, features_dim, dataset, device=None):
     """main.py:727-760 -> (relation, final loss, edge_dictionary, destination_dictionary)."""
     relation = int(relation)
-    device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     first = not source_nodes
     ei = _np(data.edge_index)
     if first:                                                          # main.py:733-735
