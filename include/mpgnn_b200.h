@@ -157,6 +157,33 @@ int mpgnn_score_relation(const mpgnn_graph* g, int64_t relation, float* d_w, con
                          const uint8_t* d_source_mask, int64_t epochs, double lr, float* d_m, float* d_v, float* d_loss_traj, int32_t* d_argmax_dst,
                          void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- device-resident candidate trainer -------------------------------------------------
+ * mpgnn_parallel_multiple (main.py:1117-1134) for ONE metapath: builds the MPNetm stack
+ * (model.py:179-228: one conv per hop, relu + dropout, fc1, relu, fc2, log_softmax), then
+ * run() performs `epochs` x (mpgnn_train, mpgnn_validation) -- forward, nll on the train index,
+ * backward, Adam, eval forward, validation nll, macro-F1 on train and validation -- on the device,
+ * the whole epoch captured once in a CUDA graph (use_graph != 0).  Parameters are exchanged as one
+ * flat fp32 array in state_dict order with torch layouts: per hop weight[f_in,H], root[f_in,H],
+ * bias[H]; fc1.weight[H,H], fc1.bias[H], fc2.weight[C,H], fc2.bias[C].  set_params also resets the
+ * optimiser state and the epoch counter.  h_trace (may be NULL) receives [epochs_done][4] doubles:
+ * train loss, validation loss, train macro-F1, validation macro-F1 per epoch; *h_last_val_f1 is
+ * what the reference returns.  d_x and the index arrays must stay alive while the trainer is used. */
+typedef struct mpgnn_trainer mpgnn_trainer;
+int mpgnn_trainer_create(const mpgnn_graph* g, const float* d_x, int64_t f_in, int64_t hidden, int64_t num_classes,
+                         const int64_t* h_relations, int64_t n_layers, const int64_t* d_train_idx,
+                         const int64_t* d_train_y, int64_t n_train, const int64_t* d_val_idx, const int64_t* d_val_y,
+                         int64_t n_val, double dropout_p, uint64_t seed, uint32_t flags, int64_t max_epochs,
+                         mpgnn_trainer** out);
+void mpgnn_trainer_free(mpgnn_trainer* t);
+int64_t mpgnn_trainer_num_params(const mpgnn_trainer* t);
+int mpgnn_trainer_set_params(mpgnn_trainer* t, const float* d_flat, void* stream);
+int mpgnn_trainer_get_params(const mpgnn_trainer* t, float* d_flat, void* stream);
+int mpgnn_trainer_run(mpgnn_trainer* t, int64_t epochs, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, int use_graph, void* stream, double* h_trace, double* h_last_val_f1);
+/* nll + macro-F1 of the current parameters on another index set (mpgnn_test, main.py:1102-1115) */
+int mpgnn_trainer_evaluate(mpgnn_trainer* t, const int64_t* d_idx, const int64_t* d_y, int64_t n_idx, void* stream,
+                           float* h_loss, double* h_f1);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,8 @@ void graph_free(mpgnn_graph_impl* g);
 int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out);
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
-            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s);
+            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s,
+            const uint64_t* offset_ptr);
 int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y, const float* gy,
             int64_t f_in, const float* w, const float* root, int64_t f_out, uint32_t flags, double p, float* gx,
             float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes, cudaStream_t s);
@@ -91,6 +92,20 @@ int score_relation(const mpgnn_graph_impl* g, int64_t rel, float* w, const float
                    int64_t epochs, double lr,
                    float* m, float* v, float* loss_traj, int32_t* argmax_dst, void* ws_ptr, int64_t ws_bytes,
                    cudaStream_t s);
+
+struct Trainer;
+int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int64_t hidden, int64_t classes,
+                   const int64_t* h_rel, int64_t n_layers, const int64_t* train_idx, const int64_t* train_y,
+                   int64_t n_train, const int64_t* val_idx, const int64_t* val_y, int64_t n_val, double dropout_p,
+                   uint64_t seed, uint32_t flags, int64_t max_epochs, Trainer** out);
+void trainer_free(Trainer* t);
+int64_t trainer_num_params(const Trainer* t);
+int trainer_set_params(Trainer* t, const float* d_flat, cudaStream_t s);
+int trainer_get_params(const Trainer* t, float* d_flat, cudaStream_t s);
+int trainer_run(Trainer* t, int64_t epochs, double lr, double b1, double b2, double eps, double wd, int use_graph,
+                cudaStream_t s, double* h_trace, double* h_last_val_f1);
+int trainer_evaluate(Trainer* t, const int64_t* d_idx, const int64_t* d_y, int64_t n_idx, cudaStream_t s, float* h_loss,
+                     double* h_f1);
 
 }  // namespace mpgnn
 
@@ -223,7 +238,7 @@ int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int6
                   uint64_t seed, uint64_t offset, const uint8_t* d_mask_bits, float* d_h, float* d_y,
                   void* d_workspace, int64_t workspace_bytes, void* stream) {
   return hop_fwd(impl(g), relation, d_x, f_in, d_w, d_root, d_bias, f_out, flags, dropout_p, seed, offset,
-                 d_mask_bits, d_h, d_y, d_workspace, workspace_bytes, stream_of(stream));
+                 d_mask_bits, d_h, d_y, d_workspace, workspace_bytes, stream_of(stream), nullptr);
 }
 
 int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, const float* d_h, const float* d_y,
@@ -309,6 +324,35 @@ int mpgnn_score_relation(const mpgnn_graph* g, int64_t relation, float* d_w, con
                          void* d_workspace, int64_t workspace_bytes, void* stream) {
   return score_relation(impl(g), relation, d_w, d_labels, d_source_mask, epochs, lr, d_m, d_v, d_loss_traj, d_argmax_dst, d_workspace,
                         workspace_bytes, stream_of(stream));
+}
+
+int mpgnn_trainer_create(const mpgnn_graph* g, const float* d_x, int64_t f_in, int64_t hidden, int64_t num_classes,
+                         const int64_t* h_relations, int64_t n_layers, const int64_t* d_train_idx,
+                         const int64_t* d_train_y, int64_t n_train, const int64_t* d_val_idx, const int64_t* d_val_y,
+                         int64_t n_val, double dropout_p, uint64_t seed, uint32_t flags, int64_t max_epochs,
+                         mpgnn_trainer** out) {
+  Trainer* t = nullptr;
+  int rc = trainer_create(impl(g), d_x, f_in, hidden, num_classes, h_relations, n_layers, d_train_idx, d_train_y,
+                          n_train, d_val_idx, d_val_y, n_val, dropout_p, seed, flags, max_epochs, &t);
+  if (rc == MPGNN_OK) *out = reinterpret_cast<mpgnn_trainer*>(t);
+  return rc;
+}
+void mpgnn_trainer_free(mpgnn_trainer* t) { trainer_free(reinterpret_cast<Trainer*>(t)); }
+int64_t mpgnn_trainer_num_params(const mpgnn_trainer* t) { return trainer_num_params(reinterpret_cast<const Trainer*>(t)); }
+int mpgnn_trainer_set_params(mpgnn_trainer* t, const float* d_flat, void* stream) {
+  return trainer_set_params(reinterpret_cast<Trainer*>(t), d_flat, stream_of(stream));
+}
+int mpgnn_trainer_get_params(const mpgnn_trainer* t, float* d_flat, void* stream) {
+  return trainer_get_params(reinterpret_cast<const Trainer*>(t), d_flat, stream_of(stream));
+}
+int mpgnn_trainer_run(mpgnn_trainer* t, int64_t epochs, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, int use_graph, void* stream, double* h_trace, double* h_last_val_f1) {
+  return trainer_run(reinterpret_cast<Trainer*>(t), epochs, lr, beta1, beta2, eps, weight_decay, use_graph,
+                     stream_of(stream), h_trace, h_last_val_f1);
+}
+int mpgnn_trainer_evaluate(mpgnn_trainer* t, const int64_t* d_idx, const int64_t* d_y, int64_t n_idx, void* stream,
+                           float* h_loss, double* h_f1) {
+  return trainer_evaluate(reinterpret_cast<Trainer*>(t), d_idx, d_y, n_idx, stream_of(stream), h_loss, h_f1);
 }
 
 }  // extern "C"

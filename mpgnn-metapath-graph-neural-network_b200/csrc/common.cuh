@@ -103,6 +103,7 @@ struct GemmRowsArgs {
   float dropout_p; float dropout_scale;   // scale = (float)(1/(1-p)) formed in double on the host
   uint32_t dropout_thr16;                 // keep iff 16-bit random lane >= thr16 = round(p*65536)
   uint64_t seed; uint64_t offset; const uint8_t* mask_bits;
+  const uint64_t* offset_ptr;             // optional device word added to `offset` (CUDA-graph replays)
   float* out; int64_t ldo;
 };
 int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s);

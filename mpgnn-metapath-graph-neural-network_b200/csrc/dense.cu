@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
   }
 
   const float scale = a.dropout_mode ? a.dropout_scale : 1.f;
+  const uint64_t drop_off = a.offset + (a.offset_ptr != nullptr ? *a.offset_ptr : 0ull);
   const int64_t mask_ld = (a.n + 7) / 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.gate != nullptr) v = (__ldg(a.gate + row * a.ldgate + col) > 0.f) ? v : 0.f;
       if (a.dropout_mode == 1) {
-        v = dropout_keep(a.seed, a.offset, (uint64_t)row * (uint64_t)a.n + (uint64_t)col, a.dropout_thr16) ? v * scale : 0.f;
+        v = dropout_keep(a.seed, drop_off, (uint64_t)row * (uint64_t)a.n + (uint64_t)col, a.dropout_thr16) ? v * scale : 0.f;
       } else if (a.dropout_mode == 2) {
         const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
         v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;

@@ -36,7 +36,8 @@ int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
 
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
-            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s) {
+            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s,
+            const uint64_t* offset_ptr) {
   MPGNN_REQUIRE(g && x && w && root && h && y, MPGNN_EINVAL, "hop_fwd: NULL argument");
   MPGNN_REQUIRE(rel >= 0 && rel < g->r, MPGNN_ERANGE, "hop_fwd: relation %lld outside [0,%lld)", (long long)rel,
                 (long long)g->r);
@@ -66,6 +67,7 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   a.dropout_mode = drop_seed ? 1 : (drop_mask ? 2 : 0);
   a.dropout_p = (float)p; a.dropout_scale = (float)(1.0 / (1.0 - p));
   a.dropout_thr16 = dropout_threshold16(p); a.seed = seed; a.offset = offset; a.mask_bits = mask_bits;
+  a.offset_ptr = offset_ptr;
   a.out = y; a.ldo = f_out;
   if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
     ScopedTimer tm("proj_fwd_tcgen05", s);

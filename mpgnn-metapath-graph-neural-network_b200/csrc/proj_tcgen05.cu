@@ -53,7 +53,7 @@ struct Params {
   int relu;
   const int32_t* deg_ptr; int deg_cols;
   int dropout_mode; uint32_t dropout_thr16; float dropout_scale; uint64_t seed; uint64_t offset;
-  const uint8_t* mask_bits;
+  const uint8_t* mask_bits; const uint64_t* offset_ptr;
   float* out; int64_t ldo;
 };
 
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     float* stg = sm_stg + ew * 32 * kStgLd;
     const int64_t mask_ld = (p.n + 7) / 8;
     const bool do_drop_seed = p.dropout_mode == 1, do_drop_mask = p.dropout_mode == 2;
+    const uint64_t drop_off = p.offset + (p.offset_ptr != nullptr ? *p.offset_ptr : 0ull);
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int buf = ti & 1;
       const uint32_t ph = (uint32_t)((ti >> 1) & 1);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
             const int e0 = hp * 16 + 4 * q;                 // first of 4 consecutive elements
             uint64_t rnd = 0;
             if (do_drop_seed)
-              rnd = dropout_word(p.seed, p.offset, ((uint64_t)row * (uint64_t)p.n + (uint64_t)(col0 + e0)) >> 2);
+              rnd = dropout_word(p.seed, drop_off, ((uint64_t)row * (uint64_t)p.n + (uint64_t)(col0 + e0)) >> 2);
             uint32_t mbits = 0;
             if (do_drop_mask && row < p.m) {
               const int c = col0 + e0;                      // multiple of 4: the nibble of one byte
@@ -355,7 +356,7 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   p.bias = a.bias; p.relu = a.relu;
   p.deg_ptr = a.deg_ptr; p.deg_cols = a.deg_ptr ? (int)a.deg_cols : 0;
   p.dropout_mode = a.dropout_mode; p.dropout_thr16 = a.dropout_thr16; p.dropout_scale = a.dropout_scale;
-  p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits;
+  p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits; p.offset_ptr = a.offset_ptr;
   p.out = a.out; p.ldo = a.ldo;
   const int64_t n_tiles = ceil_div(a.m, tc::kTileM);
   int64_t grid = n_tiles * n_slices;

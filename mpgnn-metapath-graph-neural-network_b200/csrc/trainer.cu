@@ -1,0 +1,359 @@
+// Device-resident candidate trainer: one call scores one candidate metapath the way
+// mpgnn_parallel_multiple does (main.py:1117-1134) -- `epochs` x (mpgnn_train, mpgnn_validation) of
+// an MPNetm with ONE metapath (model.py:179-228) -- without returning to the host between epochs.
+// The whole epoch (train forward, loss, backward, Adam, eval forward, validation loss, macro-F1)
+// is captured once in a CUDA graph and replayed: configs C1-C3 are launch-bound, so
+// the per-epoch cost becomes one graph launch instead of ~60 kernel launches + a host sync.
+// Everything that changes from epoch to epoch (Adam step, dropout offsets, trace slot) lives in
+// device words advanced by the first kernel of the graph.
+#include <vector>
+
+#include "common.cuh"
+
+namespace mpgnn {
+
+int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out);
+int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
+            const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
+            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s,
+            const uint64_t* offset_ptr);
+int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y, const float* gy,
+            int64_t f_in, const float* w, const float* root, int64_t f_out, uint32_t flags, double p, float* gx,
+            float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes, cudaStream_t s);
+int launch_logsoftmax_nll(const float* logits, int64_t n, int64_t c, const int64_t* idx, const int64_t* y,
+                          int64_t n_idx, float* logp, float* loss, float* glogits, void* ws, int64_t ws_bytes,
+                          cudaStream_t s);
+int launch_macro_f1(const float* logp, int64_t c, const int64_t* idx, const int64_t* y, int64_t n_idx, int32_t* cm,
+                    double* f1, cudaStream_t s);
+
+struct TrainerState {      // device words advanced once per epoch
+  int64_t epoch;           // 1-based after the bump
+  uint64_t drop_off[8];    // per-layer dropout offset of this epoch: epoch * n_layers + layer
+};
+
+__global__ void trainer_bump_kernel(TrainerState* st, int n_layers) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->epoch += 1;
+    for (int k = 0; k < n_layers; ++k) st->drop_off[k] = (uint64_t)st->epoch * (uint64_t)n_layers + (uint64_t)k;
+  }
+}
+
+// torch.optim.Adam step with the step count read from the device (graph replay safe)
+__global__ void trainer_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                    float* __restrict__ v, int64_t n, const TrainerState* __restrict__ st, double lr,
+                                    double b1, double b2, double eps, double wd) {
+  const double t = (double)st->epoch;
+  const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+  const float step_size = (float)(lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const float omb1 = (float)(1.0 - b1), fb2 = (float)b2, omb2 = (float)(1.0 - b2), feps = (float)eps, fwd = (float)wd;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (fwd != 0.f) gi = fmaf(fwd, pi, gi);
+    const float mi = m[i] + (gi - m[i]) * omb1;
+    const float vi = v[i] * fb2 + omb2 * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + feps));
+  }
+}
+
+__global__ void trainer_trace_kernel(const TrainerState* st, const float* loss_train, const float* loss_val,
+                                     const double* f1_train, const double* f1_val, double* trace, int64_t capacity) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int64_t e = st->epoch - 1;
+    if (e >= 0 && e < capacity) {
+      trace[4 * e + 0] = (double)*loss_train;
+      trace[4 * e + 1] = (double)*loss_val;
+      trace[4 * e + 2] = *f1_train;
+      trace[4 * e + 3] = *f1_val;
+    }
+  }
+}
+
+struct Trainer {
+  const mpgnn_graph_impl* g;
+  const float* x;
+  int64_t n, f_in, hidden, classes;
+  int n_layers;
+  int64_t rel[8];
+  const int64_t *train_idx, *train_y, *val_idx, *val_y;
+  int64_t n_train, n_val;
+  double dropout_p;
+  uint64_t seed;
+  uint32_t flags;
+  // parameters: per layer [W (fin x H), root (fin x H), bias (H)], then W1t (H x H), b1 (H), W2t (H x C), b2 (C)
+  int64_t n_params;
+  int64_t off_w[8], off_root[8], off_bias[8], off_w1, off_b1, off_w2, off_b2;
+  float *params, *grads, *adam_m, *adam_v;
+  float *h[8], *y[8];           // aggregated inputs and activations per layer
+  float *gxa, *gxb;             // ping-pong activation gradients
+  float *a1, *lg, *logp, *glg, *gz1, *packed;
+  float *loss_train, *loss_val;
+  double *f1_train, *f1_val, *trace;
+  int64_t trace_capacity;
+  int32_t* cm;
+  TrainerState* st;
+  void* ws;
+  int64_t ws_bytes;
+  cudaGraphExec_t exec;
+  double cap_lr, cap_b1, cap_b2, cap_eps, cap_wd;
+};
+
+static int64_t trainer_ws_bytes(const Trainer& t) {
+  int64_t a = hop_workspace_bytes(t.n, t.f_in, t.hidden), b = hop_workspace_bytes(t.n, t.hidden, t.hidden);
+  int64_t hop = a > b ? a : b;
+  int64_t kmax = t.hidden > t.classes ? t.hidden : t.classes;
+  int64_t tn = gemm_tn_partial_floats(t.n, kmax + 1, kmax) * 4 + 4096;
+  return (hop > tn ? hop : tn) + 1024 * 8;
+}
+
+template <typename T>
+static cudaError_t dev_alloc(T** p, int64_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), (size_t)(count > 0 ? count : 1) * sizeof(T));
+}
+
+void trainer_free(Trainer* t) {
+  if (!t) return;
+  if (t->exec) cudaGraphExecDestroy(t->exec);
+  float* bufs[] = {t->params, t->grads, t->adam_m, t->adam_v, t->gxa, t->gxb, t->a1, t->lg, t->logp, t->glg,
+                   t->gz1, t->packed, t->loss_train, t->loss_val};
+  for (float* b : bufs) cudaFree(b);
+  for (int k = 0; k < 8; ++k) {
+    cudaFree(t->h[k]);
+    cudaFree(t->y[k]);
+  }
+  cudaFree(t->f1_train); cudaFree(t->f1_val); cudaFree(t->trace); cudaFree(t->cm); cudaFree(t->st); cudaFree(t->ws);
+  delete t;
+}
+
+int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int64_t hidden, int64_t classes,
+                   const int64_t* h_rel, int64_t n_layers, const int64_t* train_idx, const int64_t* train_y,
+                   int64_t n_train, const int64_t* val_idx, const int64_t* val_y, int64_t n_val, double dropout_p,
+                   uint64_t seed, uint32_t flags, int64_t max_epochs, Trainer** out) {
+  MPGNN_REQUIRE(g && x && h_rel && train_idx && train_y && val_idx && val_y && out, MPGNN_EINVAL, "trainer: NULL argument");
+  MPGNN_REQUIRE(n_layers >= 1 && n_layers <= 8, MPGNN_ENOTSUP, "trainer: metapath length %lld outside [1,8]", (long long)n_layers);
+  MPGNN_REQUIRE(f_in >= 1 && hidden >= 1 && classes >= 1 && classes <= 64 && n_train > 0 && n_val > 0, MPGNN_EINVAL, "trainer: bad sizes");
+  MPGNN_REQUIRE(dropout_p >= 0.0 && dropout_p < 1.0, MPGNN_EINVAL, "trainer: dropout p=%g", dropout_p);
+  for (int64_t k = 0; k < n_layers; ++k)
+    MPGNN_REQUIRE(h_rel[k] >= 0 && h_rel[k] < g->r, MPGNN_ERANGE, "trainer: relation %lld outside [0,%lld)", (long long)h_rel[k], (long long)g->r);
+  Trainer* t = new Trainer();
+  memset(t, 0, sizeof(*t));
+  t->g = g; t->x = x; t->n = g->n; t->f_in = f_in; t->hidden = hidden; t->classes = classes;
+  t->n_layers = (int)n_layers;
+  for (int k = 0; k < n_layers; ++k) t->rel[k] = h_rel[k];
+  t->train_idx = train_idx; t->train_y = train_y; t->n_train = n_train;
+  t->val_idx = val_idx; t->val_y = val_y; t->n_val = n_val;
+  t->dropout_p = dropout_p; t->seed = seed; t->flags = flags;
+  int64_t off = 0;
+  for (int k = 0; k < n_layers; ++k) {
+    const int64_t fi = k == 0 ? f_in : hidden;
+    t->off_w[k] = off; off += fi * hidden;
+    t->off_root[k] = off; off += fi * hidden;
+    t->off_bias[k] = off; off += hidden;
+  }
+  t->off_w1 = off; off += hidden * hidden;
+  t->off_b1 = off; off += hidden;
+  t->off_w2 = off; off += hidden * classes;
+  t->off_b2 = off; off += classes;
+  t->n_params = off;
+  t->trace_capacity = max_epochs > 0 ? max_epochs : 1;
+  const int64_t n = t->n;
+  cudaError_t ce = cudaSuccess;
+#define TR_ALLOC(ptr, count) if (ce == cudaSuccess) ce = dev_alloc(&(ptr), (count))
+  TR_ALLOC(t->params, off); TR_ALLOC(t->grads, off); TR_ALLOC(t->adam_m, off); TR_ALLOC(t->adam_v, off);
+  for (int k = 0; k < n_layers; ++k) {
+    TR_ALLOC(t->h[k], n * (k == 0 ? f_in : hidden));
+    TR_ALLOC(t->y[k], n * hidden);
+  }
+  TR_ALLOC(t->gxa, n * hidden); TR_ALLOC(t->gxb, n * hidden);
+  TR_ALLOC(t->a1, n * hidden); TR_ALLOC(t->lg, n * classes); TR_ALLOC(t->logp, n * classes);
+  TR_ALLOC(t->glg, n * classes); TR_ALLOC(t->gz1, n * hidden);
+  TR_ALLOC(t->packed, hidden * (hidden > classes ? hidden : classes));
+  TR_ALLOC(t->loss_train, 1); TR_ALLOC(t->loss_val, 1);
+  TR_ALLOC(t->f1_train, 1); TR_ALLOC(t->f1_val, 1); TR_ALLOC(t->trace, 4 * t->trace_capacity);
+  TR_ALLOC(t->cm, classes * classes); TR_ALLOC(t->st, 1);
+  t->ws_bytes = trainer_ws_bytes(*t);
+  if (ce == cudaSuccess) ce = cudaMalloc(&t->ws, (size_t)t->ws_bytes);
+#undef TR_ALLOC
+  if (ce != cudaSuccess) {
+    set_error("trainer: allocation failed: %s", cudaGetErrorString(ce));
+    trainer_free(t);
+    return MPGNN_ECUDA;
+  }
+  *out = t;
+  return MPGNN_OK;
+}
+
+// one forward pass; train=true applies the seeded dropout and produces glg for the backward
+static int trainer_forward(Trainer* t, bool train, cudaStream_t s) {
+  const int64_t n = t->n, H = t->hidden, C = t->classes;
+  const float* in = t->x;
+  for (int k = 0; k < t->n_layers; ++k) {
+    const int64_t fi = k == 0 ? t->f_in : H;
+    uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16));
+    if (train && t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
+    MPGNN_PROPAGATE(hop_fwd(t->g, t->rel[k], in, fi, t->params + t->off_w[k], t->params + t->off_root[k],
+                            t->params + t->off_bias[k], H, fl, t->dropout_p, t->seed, 0, nullptr, t->h[k], t->y[k],
+                            t->ws, t->ws_bytes, s, &t->st->drop_off[k]));
+    in = t->y[k];
+  }
+  GemmRowsArgs a{};
+  a.a1 = in; a.lda1 = H; a.k1 = H; a.b = t->params + t->off_w1; a.m = n; a.n = H;
+  a.bias = t->params + t->off_b1; a.relu = 1; a.out = t->a1; a.ldo = H;
+  MPGNN_PROPAGATE(launch_gemm_rows(a, s));                                   // a1 = relu(E W1t + b1)
+  GemmRowsArgs b{};
+  b.a1 = t->a1; b.lda1 = H; b.k1 = H; b.b = t->params + t->off_w2; b.m = n; b.n = C;
+  b.bias = t->params + t->off_b2; b.out = t->lg; b.ldo = C;
+  MPGNN_PROPAGATE(launch_gemm_rows(b, s));                                   // logits
+  if (train)
+    return launch_logsoftmax_nll(t->lg, n, C, t->train_idx, t->train_y, t->n_train, t->logp, t->loss_train, t->glg,
+                                 t->ws, t->ws_bytes, s);
+  return launch_logsoftmax_nll(t->lg, n, C, t->val_idx, t->val_y, t->n_val, t->logp, t->loss_val, nullptr, t->ws,
+                               t->ws_bytes, s);
+}
+
+static int trainer_backward(Trainer* t, cudaStream_t s) {
+  const int64_t n = t->n, H = t->hidden, C = t->classes;
+  const float* e_last = t->y[t->n_layers - 1];
+  Workspace ws(t->ws, t->ws_bytes);
+  const int64_t kmax = H > C ? H : C;
+  const int64_t pf = gemm_tn_partial_floats(n, kmax + 1, kmax);
+  float* partials = ws.take<float>(pf);
+  MPGNN_REQUIRE(partials != nullptr, MPGNN_EINVAL, "trainer: workspace too small");
+  // fc2: [gW2t; gb2] = a1^T glg
+  GemmTnArgs t2{};
+  t2.a1 = t->a1; t2.lda1 = H; t2.k1 = H; t2.ones_row = 1; t2.b = t->glg; t2.ldb = C; t2.n = C; t2.m = n;
+  t2.out1 = t->grads + t->off_w2; t2.ldo1 = C; t2.out_ones = t->grads + t->off_b2;
+  t2.partials = partials; t2.partial_capacity_floats = pf;
+  MPGNN_PROPAGATE(launch_gemm_tn(t2, s));
+  // g_z1 = (glg W2t^T) * [a1 > 0]
+  MPGNN_PROPAGATE(launch_pack_b(t->packed, H, t->params + t->off_w2, 1, C, C, H, s));   // B(k=c, n=h) = W2t[h*C + c]
+  GemmRowsArgs a{};
+  a.a1 = t->glg; a.lda1 = C; a.k1 = C; a.b = t->packed; a.m = n; a.n = H;
+  a.gate = t->a1; a.ldgate = H; a.out = t->gz1; a.ldo = H;
+  MPGNN_PROPAGATE(launch_gemm_rows(a, s));
+  // fc1: [gW1t; gb1] = E^T g_z1
+  GemmTnArgs t1{};
+  t1.a1 = e_last; t1.lda1 = H; t1.k1 = H; t1.ones_row = 1; t1.b = t->gz1; t1.ldb = H; t1.n = H; t1.m = n;
+  t1.out1 = t->grads + t->off_w1; t1.ldo1 = H; t1.out_ones = t->grads + t->off_b1;
+  t1.partials = partials; t1.partial_capacity_floats = pf;
+  MPGNN_PROPAGATE(launch_gemm_tn(t1, s));
+  // g_E = g_z1 W1t^T
+  MPGNN_PROPAGATE(launch_pack_b(t->packed, H, t->params + t->off_w1, 1, H, H, H, s));   // B(k=o, n=i) = W1t[i*H + o]
+  GemmRowsArgs b{};
+  b.a1 = t->gz1; b.lda1 = H; b.k1 = H; b.b = t->packed; b.m = n; b.n = H; b.out = t->gxa; b.ldo = H;
+  MPGNN_PROPAGATE(launch_gemm_rows(b, s));
+  float* gy = t->gxa;
+  float* gx = t->gxb;
+  for (int k = t->n_layers - 1; k >= 0; --k) {
+    const int64_t fi = k == 0 ? t->f_in : H;
+    const float* in = k == 0 ? t->x : t->y[k - 1];
+    uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16));
+    if (t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
+    if (k > 0) fl |= MPGNN_F_NEED_GX;
+    MPGNN_PROPAGATE(hop_bwd(t->g, t->rel[k], in, t->h[k], t->y[k], gy, fi, t->params + t->off_w[k],
+                            t->params + t->off_root[k], H, fl, t->dropout_p, k > 0 ? gx : nullptr,
+                            t->grads + t->off_w[k], t->grads + t->off_root[k], t->grads + t->off_bias[k], t->ws,
+                            t->ws_bytes, s));
+    float* tmp = gy; gy = gx; gx = tmp;
+  }
+  return MPGNN_OK;
+}
+
+static int trainer_epoch(Trainer* t, double lr, double b1, double b2, double eps, double wd, cudaStream_t s) {
+  trainer_bump_kernel<<<1, 32, 0, s>>>(t->st, t->n_layers);
+  MPGNN_LAUNCH_CHECK();
+  MPGNN_PROPAGATE(trainer_forward(t, true, s));                 // mpgnn_train: forward, nll on train idx
+  MPGNN_PROPAGATE(trainer_backward(t, s));                      // backward
+  int64_t blocks = ceil_div(t->n_params, 256);
+  trainer_adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(t->params, t->grads, t->adam_m, t->adam_v, t->n_params, t->st,
+                                                       lr, b1, b2, eps, wd);
+  MPGNN_LAUNCH_CHECK();
+  MPGNN_PROPAGATE(trainer_forward(t, false, s));                // mpgnn_validation: eval forward, nll on val idx
+  MPGNN_PROPAGATE(launch_macro_f1(t->logp, t->classes, t->train_idx, t->train_y, t->n_train, t->cm, t->f1_train, s));
+  MPGNN_PROPAGATE(launch_macro_f1(t->logp, t->classes, t->val_idx, t->val_y, t->n_val, t->cm, t->f1_val, s));
+  trainer_trace_kernel<<<1, 32, 0, s>>>(t->st, t->loss_train, t->loss_val, t->f1_train, t->f1_val, t->trace,
+                                        t->trace_capacity);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+int trainer_run(Trainer* t, int64_t epochs, double lr, double b1, double b2, double eps, double wd, int use_graph,
+                cudaStream_t s, double* h_trace, double* h_last_val_f1) {
+  MPGNN_REQUIRE(t != nullptr && epochs >= 1, MPGNN_EINVAL, "trainer_run: bad arguments");
+  if (use_graph) {
+    const bool stale = t->exec == nullptr || lr != t->cap_lr || b1 != t->cap_b1 || b2 != t->cap_b2 || eps != t->cap_eps ||
+                       wd != t->cap_wd;
+    if (stale) {
+      if (t->exec) { cudaGraphExecDestroy(t->exec); t->exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      MPGNN_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      int rc = trainer_epoch(t, lr, b1, b2, eps, wd, s);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc != MPGNN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      MPGNN_CUDA_CHECK(ce);
+      ce = cudaGraphInstantiate(&t->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      MPGNN_CUDA_CHECK(ce);
+      t->cap_lr = lr; t->cap_b1 = b1; t->cap_b2 = b2; t->cap_eps = eps; t->cap_wd = wd;
+    }
+    for (int64_t e = 0; e < epochs; ++e) MPGNN_CUDA_CHECK(cudaGraphLaunch(t->exec, s));
+  } else {
+    for (int64_t e = 0; e < epochs; ++e) MPGNN_PROPAGATE(trainer_epoch(t, lr, b1, b2, eps, wd, s));
+  }
+  if (h_trace != nullptr || h_last_val_f1 != nullptr) {
+    TrainerState hs;
+    MPGNN_CUDA_CHECK(cudaMemcpyAsync(&hs, t->st, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
+    int64_t done = hs.epoch < t->trace_capacity ? hs.epoch : t->trace_capacity;
+    if (h_trace != nullptr && done > 0)
+      MPGNN_CUDA_CHECK(cudaMemcpy(h_trace, t->trace, (size_t)done * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_last_val_f1 != nullptr) MPGNN_CUDA_CHECK(cudaMemcpy(h_last_val_f1, t->f1_val, sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return MPGNN_OK;
+}
+
+// flat parameter exchange in state_dict order with torch layouts ([out,in] for fc weights);
+// internally the fc weights are stored transposed ([in,out]) so the forward needs no repacking
+int trainer_set_params(Trainer* t, const float* d_flat, cudaStream_t s) {
+  MPGNN_REQUIRE(t && d_flat, MPGNN_EINVAL, "trainer_set_params: NULL argument");
+  const int64_t H = t->hidden, C = t->classes;
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(t->params, d_flat, (size_t)t->n_params * 4, cudaMemcpyDeviceToDevice, s));
+  MPGNN_PROPAGATE(launch_pack_b(t->params + t->off_w1, H, d_flat + t->off_w1, 1, H, H, H, s));   // W1t[i][o] = W1[o][i]
+  MPGNN_PROPAGATE(launch_pack_b(t->params + t->off_w2, C, d_flat + t->off_w2, 1, H, H, C, s));   // W2t[h][c] = W2[c][h]
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(t->adam_m, 0, (size_t)t->n_params * 4, s));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(t->adam_v, 0, (size_t)t->n_params * 4, s));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(t->st, 0, sizeof(TrainerState), s));
+  return MPGNN_OK;
+}
+
+int trainer_get_params(const Trainer* t, float* d_flat, cudaStream_t s) {
+  MPGNN_REQUIRE(t && d_flat, MPGNN_EINVAL, "trainer_get_params: NULL argument");
+  const int64_t H = t->hidden, C = t->classes;
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(d_flat, t->params, (size_t)t->n_params * 4, cudaMemcpyDeviceToDevice, s));
+  MPGNN_PROPAGATE(launch_pack_b(d_flat + t->off_w1, H, t->params + t->off_w1, 1, H, H, H, s));   // W1[o][i] = W1t[i][o]
+  MPGNN_PROPAGATE(launch_pack_b(d_flat + t->off_w2, H, t->params + t->off_w2, 1, C, C, H, s));   // W2[c][h] = W2t[h][c]
+  return MPGNN_OK;
+}
+
+int64_t trainer_num_params(const Trainer* t) { return t ? t->n_params : 0; }
+
+// macro-F1 / nll of the CURRENT parameters on an arbitrary index set (mpgnn_test, main.py:1102-1115)
+int trainer_evaluate(Trainer* t, const int64_t* d_idx, const int64_t* d_y, int64_t n_idx, cudaStream_t s, float* h_loss,
+                     double* h_f1) {
+  MPGNN_REQUIRE(t && d_idx && d_y && n_idx > 0, MPGNN_EINVAL, "trainer_evaluate: bad arguments");
+  const int64_t *vi = t->val_idx, *vy = t->val_y, vn = t->n_val;
+  t->val_idx = d_idx; t->val_y = d_y; t->n_val = n_idx;
+  int rc = trainer_forward(t, false, s);
+  if (rc == MPGNN_OK) rc = launch_macro_f1(t->logp, t->classes, d_idx, d_y, n_idx, t->cm, t->f1_val, s);
+  t->val_idx = vi; t->val_y = vy; t->n_val = vn;
+  MPGNN_PROPAGATE(rc);
+  MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (h_loss) MPGNN_CUDA_CHECK(cudaMemcpy(h_loss, t->loss_val, sizeof(float), cudaMemcpyDeviceToHost));
+  if (h_f1) MPGNN_CUDA_CHECK(cudaMemcpy(h_f1, t->f1_val, sizeof(double), cudaMemcpyDeviceToHost));
+  return MPGNN_OK;
+}
+
+}  // namespace mpgnn

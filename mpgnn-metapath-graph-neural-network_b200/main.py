@@ -7,6 +7,7 @@ host (as in the reference) -- they are staged to the model's device once and cac
 bag.
 """
 import ctypes
+import weakref
 
 import numpy as np
 import torch
@@ -110,6 +111,98 @@ def mpgnn_test(model, data, class_weight):
     return loss_test, f1_test
 
 
+class CandidateTrainer:
+    """Device-resident training of ONE candidate metapath (the native `mpgnn_trainer_*` entry points):
+    the 999 x (mpgnn_train, mpgnn_validation) loop of main.py:1117-1134 as CUDA-graph replays."""
+
+    def __init__(self, data_mpgnn, input_dim, hidden_dim, ll_output_dim, metapath, device=None, dropout_p=0.6,
+                 seed=None, precision="fp32", max_epochs=EPOCHS_PER_CANDIDATE):
+        lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.st = _staged(data_mpgnn, self.device)
+        self.metapath = [int(r) for r in metapath]
+        self.dims = (int(input_dim), int(hidden_dim), int(ll_output_dim))
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        flags = _lib.F_TF32X3 if precision == "tf32x3" else 0
+        rel = np.asarray(self.metapath, dtype=np.int64)
+        handle = ctypes.c_void_p()
+        st = self.st
+        with torch.cuda.device(self.device):
+            _lib.check(lib.mpgnn_trainer_create(
+                st["graph"].handle, _lib.ptr(st["x"]), self.dims[0], self.dims[1], self.dims[2],
+                rel.ctypes.data_as(ctypes.c_void_p), len(rel), _lib.ptr(st["train_idx"]), _lib.ptr(st["train_y"]),
+                st["train_idx"].numel(), _lib.ptr(st["val_idx"]), _lib.ptr(st["val_y"]), st["val_idx"].numel(),
+                float(dropout_p), int(seed), flags, int(max_epochs), ctypes.byref(handle)))
+        self._handle = handle
+        self.max_epochs = int(max_epochs)
+        self.num_params = int(lib.mpgnn_trainer_num_params(handle))
+        self._finalizer = weakref.finalize(self, lib.mpgnn_trainer_free, handle)
+
+    def _keys(self):
+        keys = []
+        for k in range(len(self.metapath)):
+            keys += ["layers_list.0.%d.weight" % k, "layers_list.0.%d.root" % k, "layers_list.0.%d.bias" % k]
+        return keys + ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+
+    def load_state_dict(self, sd):
+        """Parameters in MPNetm's state_dict layout; also resets Adam and the epoch counter."""
+        flat = torch.cat([sd[k].detach().to(torch.float32).reshape(-1).cpu() for k in self._keys()]).to(self.device)
+        assert flat.numel() == self.num_params, (flat.numel(), self.num_params)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mpgnn_trainer_set_params(self._handle, _lib.ptr(flat), _lib.current_stream()))
+            torch.cuda.current_stream().synchronize()
+
+    def state_dict(self):
+        f_in, h, c = self.dims
+        flat = torch.empty(self.num_params, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mpgnn_trainer_get_params(self._handle, _lib.ptr(flat), _lib.current_stream()))
+        flat = flat.cpu()
+        out, off = {}, 0
+        shapes = []
+        for k in range(len(self.metapath)):
+            fi = f_in if k == 0 else h
+            shapes += [(fi, h), (fi, h), (h,)]
+        shapes += [(h, h), (h,), (c, h), (c,)]
+        for key, shp in zip(self._keys(), shapes):
+            cnt = int(np.prod(shp))
+            out[key] = flat[off:off + cnt].view(*shp).clone()
+            off += cnt
+        return out
+
+    def run(self, epochs, lr=ADAM_LR, weight_decay=ADAM_WEIGHT_DECAY, use_graph=True):
+        """-> float64 array [epochs done so far, 4]: train loss, val loss, train macro-F1, val macro-F1."""
+        trace = np.zeros((self.max_epochs, 4), dtype=np.float64)
+        last = ctypes.c_double()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mpgnn_trainer_run(self._handle, int(epochs), float(lr), 0.9, 0.999, 1e-8,
+                                                     float(weight_decay), int(bool(use_graph)), _lib.current_stream(),
+                                                     trace.ctypes.data_as(ctypes.c_void_p), ctypes.byref(last)))
+        self.last_val_f1 = float(last.value)
+        return trace
+
+    def evaluate(self, split="test"):
+        idx, y = self.st[split + "_idx"], self.st[split + "_y"]
+        loss, f1 = ctypes.c_float(), ctypes.c_double()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().mpgnn_trainer_evaluate(self._handle, _lib.ptr(idx), _lib.ptr(y), idx.numel(),
+                                                          _lib.current_stream(), ctypes.byref(loss), ctypes.byref(f1)))
+        return float(loss.value), float(f1.value)
+
+
+def _train_candidate_native(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths, epochs):
+    """Single-metapath candidate on the native trainer.  The model is constructed on the CPU first so
+    that the parameter draw follows the reference's RNG order (model.py:180-201)."""
+    model = MPNetm(input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, 1, metapaths, device="cpu")
+    p = model.dropout.p
+    tr = CandidateTrainer(data_mpgnn, input_dim, hidden_dim, ll_output_dim, metapaths[0], dropout_p=p,
+                          max_epochs=epochs)
+    tr.load_state_dict(model.state_dict())
+    tr.run(epochs)
+    return tr
+
+
 def _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths, epochs):
     model = MPNetm(input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, len(metapaths), metapaths)
     optimizer = torch.optim.Adam(model.parameters(), lr=ADAM_LR, weight_decay=ADAM_WEIGHT_DECAY)
@@ -122,19 +215,28 @@ def _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_
 
 
 def mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,
-                            epochs=EPOCHS_PER_CANDIDATE):
+                            epochs=EPOCHS_PER_CANDIDATE, native=True):
     """main.py:1117-1134 -- one candidate scored: 999 x (train, validation); returns the LAST
     epoch's validation macro-F1."""
+    if native and len(metapaths) == 1 and 1 <= len(metapaths[0]) <= 8:
+        return _train_candidate_native(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
+                                       metapaths, epochs).last_val_f1
     _, _, f1_val = _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
                                     metapaths, epochs)
     return f1_val
 
 
 def mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,
-                              testing, epochs=EPOCHS_PER_CANDIDATE):
+                              testing, epochs=EPOCHS_PER_CANDIDATE, native=True):
     """main.py:1136-1160 -- same for a list of metapaths; returns test macro-F1 if `testing`."""
     if isinstance(metapaths[0], (int, np.integer)):
         metapaths = [metapaths]
+    if native and len(metapaths) == 1 and 1 <= len(metapaths[0]) <= 8:
+        tr = _train_candidate_native(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,
+                                     epochs)
+        test_loss, f1_test = tr.evaluate("test")
+        print("test loss %0.3f" % test_loss, "test macro %0.3f" % f1_test)
+        return f1_test if testing else tr.last_val_f1
     model, class_weight, f1_val = _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim,
                                                    ll_output_dim, metapaths, epochs)
     test_loss, f1_test = mpgnn_test(model, data_mpgnn, class_weight)
