@@ -98,6 +98,7 @@ struct Trainer {
   void* ws;
   int64_t ws_bytes;
   cudaGraphExec_t exec;
+  cudaStream_t own_stream;   // capture is not allowed on the legacy default stream
   double cap_lr, cap_b1, cap_b2, cap_eps, cap_wd;
 };
 
@@ -117,6 +118,7 @@ static cudaError_t dev_alloc(T** p, int64_t count) {
 void trainer_free(Trainer* t) {
   if (!t) return;
   if (t->exec) cudaGraphExecDestroy(t->exec);
+  if (t->own_stream) cudaStreamDestroy(t->own_stream);
   float* bufs[] = {t->params, t->grads, t->adam_m, t->adam_v, t->gxa, t->gxb, t->a1, t->lg, t->logp, t->glg,
                    t->gz1, t->packed, t->loss_train, t->loss_val};
   for (float* b : bufs) cudaFree(b);
@@ -283,6 +285,14 @@ static int trainer_epoch(Trainer* t, double lr, double b1, double b2, double eps
 int trainer_run(Trainer* t, int64_t epochs, double lr, double b1, double b2, double eps, double wd, int use_graph,
                 cudaStream_t s, double* h_trace, double* h_last_val_f1) {
   MPGNN_REQUIRE(t != nullptr && epochs >= 1, MPGNN_EINVAL, "trainer_run: bad arguments");
+  cudaStream_t caller = s;
+  if (use_graph && (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread)) {
+    // stream capture is not permitted on the default streams: run on a private stream, ordered after
+    // everything the caller queued so far, and drain it before returning
+    if (t->own_stream == nullptr) MPGNN_CUDA_CHECK(cudaStreamCreateWithFlags(&t->own_stream, cudaStreamNonBlocking));
+    MPGNN_CUDA_CHECK(cudaStreamSynchronize(caller));
+    s = t->own_stream;
+  }
   if (use_graph) {
     const bool stale = t->exec == nullptr || lr != t->cap_lr || b1 != t->cap_b1 || b2 != t->cap_b2 || eps != t->cap_eps ||
                        wd != t->cap_wd;
@@ -303,6 +313,7 @@ int trainer_run(Trainer* t, int64_t epochs, double lr, double b1, double b2, dou
   } else {
     for (int64_t e = 0; e < epochs; ++e) MPGNN_PROPAGATE(trainer_epoch(t, lr, b1, b2, eps, wd, s));
   }
+  if (s != caller) MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
   if (h_trace != nullptr || h_last_val_f1 != nullptr) {
     TrainerState hs;
     MPGNN_CUDA_CHECK(cudaMemcpyAsync(&hs, t->st, sizeof(hs), cudaMemcpyDeviceToHost, s));

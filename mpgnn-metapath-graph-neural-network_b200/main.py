@@ -242,3 +242,70 @@ def mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output
     test_loss, f1_test = mpgnn_test(model, data_mpgnn, class_weight)
     print("test loss %0.3f" % test_loss, "test macro %0.3f" % f1_test)
     return f1_test if testing else f1_val
+
+
+# ---------------------------------------------------------------------------------------------
+# driver (main.py:1191-1476): same CLI flags as the reference; `mpiexec -n P` becomes
+# `torchrun --nproc-per-node P -m mpgnn_b200.main ...` (one process per GPU)
+# ---------------------------------------------------------------------------------------------
+def main(args):
+    from . import data as D
+    from . import search
+    import torch.distributed as dist
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=device)
+    comm = search.Comm(device)
+    log = print if comm.rank == 0 else None
+    # every rank reads the (small) files itself: nothing to broadcast (main.py:1211-1212, 1309)
+    if args.dataset == "fb15k-237":
+        true_labels, features, edges, sources, tot_rel, binary_labels = D.load_files_fb15k237(
+            args.node_file, args.link_file, args.label_file, getattr(args, "relations_legend_file", None))
+    elif args.dataset == "synthetic":
+        true_labels, features, edges, binary_labels, tot_rel = D.load_files(args.node_file, args.link_file,
+                                                                            args.label_file)
+        sources = []
+    else:
+        raise NotImplementedError("dataset %r: only 'synthetic' and 'fb15k-237' are built" % args.dataset)
+    results = []
+    for binary_lab in binary_labels:
+        x = D.get_node_features(features)
+        input_dim = x.size(1)
+        ll_output_dim = 2 if args.dataset == "synthetic" else len(torch.unique(true_labels).tolist())
+        edge_index, edge_type = D.get_edge_index_and_type_no_reverse(edges)
+        _, train_idx, train_y, test_idx, test_y, val_idx, val_y = D.splitting_node_and_labels(
+            true_labels, features, sources, args.dataset)
+        if args.dataset == "fb15k-237":
+            x = D.sn(test_idx, val_idx, train_idx, x)
+        data_mpgnn = Data(x=x, edge_index=edge_index, edge_type=edge_type, train_idx=train_idx, test_idx=test_idx,
+                          train_y=train_y, test_y=test_y, val_idx=val_idx, val_y=val_y, num_nodes=x.size(0))
+        data = Data(x=x, edge_index=edge_index, edge_type=edge_type, labels=binary_lab.unsqueeze(-1),
+                    num_nodes=x.size(0), source_nodes_mask=list(sources))
+        res = search.greedy_search(data, data_mpgnn, input_dim, args.hidden_dim, tot_rel, args.hidden_dim,
+                                   ll_output_dim, args.dataset, comm=comm, log=log)
+        results.append(res)
+        if comm.rank == 0:
+            print("final meta: ", res["final_meta"], "test acc: ", res["test_f1"])      # main.py:1476
+    return results
+
+
+def _parse_args(argv=None):
+    import argparse
+    parser = argparse.ArgumentParser(description="learning meta-paths")                    # main.py:1489-1506
+    parser.add_argument("--hidden_dim", type=int, required=True, help="hidden dimension")
+    parser.add_argument("--dataset", type=str, required=True, help="dataset")
+    parser.add_argument("--folder", type=str, required=True, help="folder")
+    parser.add_argument("--node_file", type=str, required=True, help="node features file")
+    parser.add_argument("--link_file", type=str, required=True, help="triplets file")
+    parser.add_argument("--label_file", type=str, required=True, help="labels file")
+    parser.add_argument("--relations_legend_file", type=str, required=False, help="relations legend file")
+    parser.add_argument("--pickle_filename", type=str, required=False, help="pickle files")
+    return parser.parse_args(argv)
+
+
+if __name__ == "__main__":
+    main(_parse_args())
