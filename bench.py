@@ -239,6 +239,10 @@ def run_ours(args):
                "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e_steps,
                "ms_per_step": ms_e / e_steps}
 
+    cand = None if args.no_candidates else candidate_scoring(rank, world, dev, dist)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     hbm, tf, how = _peaks()
@@ -286,9 +290,62 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
         "extra": {"graph_build_s": build_s, "rows_per_s": n * args.steps * world / (ms * 1e-3),
-                  "mean_edges_per_hop": e_r_mean, "kernels": per_kernel, "spmm_mean_fwd_roofline": spmm_roof},
+                  "mean_edges_per_hop": e_r_mean, "kernels": per_kernel, "spmm_mean_fwd_roofline": spmm_roof,
+                  "candidate_scoring": cand},
     }
     print(json.dumps(line))
+
+
+def candidate_scoring(rank, world, dev, dist, per_rank=2):
+    """Second half of the metric: candidate metapaths scored per second, BASELINE.json configs[1] shape
+    (synthetic 100k nodes, 20 relations, length-3 metapaths, hidden 64, one-hot 2-d features): each
+    candidate = 999 x (train step + validation) of an MPNetm, exactly what mpgnn_parallel_multiple does
+    (main.py:1117-1134), on the device-resident trainer.  Candidates are sharded over the ranks."""
+    import mpgnn_b200
+    n, e, r, hidden, epochs = 100_000, 550_000, 20, 64, 999
+    g = torch.Generator().manual_seed(1)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    et = torch.randint(0, r, (e,), generator=g)
+    colour = torch.randint(0, 2, (n,), generator=g)
+    x = torch.nn.functional.one_hot(colour, 2).float()
+    y = torch.randint(0, 2, (n,), generator=g)
+    perm = torch.randperm(n, generator=g)
+    n_te, n_va = n // 10, (n - n // 10) // 5
+    data = mpgnn_b200.Data(x=x, edge_index=ei, edge_type=et, num_nodes=n,
+                           test_idx=perm[:n_te], test_y=y[perm[:n_te]], val_idx=perm[n_te:n_te + n_va],
+                           val_y=y[perm[n_te:n_te + n_va]], train_idx=perm[n_te + n_va:], train_y=y[perm[n_te + n_va:]])
+    metas = [[(3 * (rank * per_rank + c) + k) % r for k in range(3)] for c in range(per_rank)]
+    torch.manual_seed(30)
+    mpgnn_b200.mpgnn_parallel_multiple(data, 2, hidden, r, hidden, 2, [metas[0]], epochs=5)      # warm-up / staging
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    f1s = []
+    for meta in metas:
+        torch.manual_seed(30)
+        f1s.append(mpgnn_b200.mpgnn_parallel_multiple(data, 2, hidden, r, hidden, 2, [meta], epochs=epochs))
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out = {"candidates_per_s": world * per_rank / dt, "candidates": world * per_rank, "seconds": dt,
+           "epochs_per_candidate": epochs,
+           "config": "C2 shape: %d nodes / %d edges / %d relations, length-3 metapaths, hidden %d, random labels" % (n, e, r, hidden)}
+    if rank == 0 and world == 1:
+        from oracle import mpgnn_oracle as orc
+        torch.manual_seed(30)
+        sd = orc.mpnetm_init(2, hidden, 2, [metas[0]])
+        bag = {"x": x, "edge_index": ei, "edge_type": et, "train_idx": data.train_idx.tolist(), "train_y": data.train_y,
+               "val_idx": data.val_idx.tolist(), "val_y": data.val_y}
+        t1 = time.time()
+        orc.score_candidate(sd, bag, [metas[0]], epochs=3)
+        per_epoch = (time.time() - t1) / 3
+        out["cpu_port_candidates_per_s_extrapolated"] = 1.0 / (per_epoch * epochs)
+        out["cpu_port_note"] = "oracle port, 3 epochs timed on %d threads, linearly extrapolated to 999" % torch.get_num_threads()
+    return out
 
 
 def cpu_baseline(steps, warmup, budget_s, workload="c4_tenth"):
@@ -361,6 +418,7 @@ def main():
                     help="tf32x3 = fp32-parity 3xTF32 split on tcgen05 (default); fp32 = exact-fp32 SIMT projection")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-candidates", action="store_true", help="skip the candidate-scoring (C2 shape) measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
