@@ -157,6 +157,22 @@ int mpgnn_score_relation(const mpgnn_graph* g, int64_t relation, float* d_w, con
                          const uint8_t* d_source_mask, int64_t epochs, double lr, float* d_m, float* d_v, float* d_loss_traj, int32_t* d_argmax_dst,
                          void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* K5, bag mode (score_relation_bags_parallel / retrain_bags, main.py:814-917; OutputLayer.forward
+ * BAGS branch, model.py:45-72): ONE restart = `epochs` train() steps.  A bag is a list of source
+ * nodes (d_bag_ptr int32 [B+1] into d_bag_src int32, already restricted to sources that have an
+ * edge of `relation`); its prediction is max over its sources s of w[argmax_d w[d]*a_s]*a_s with
+ * a_s = <x[s], lin>.  MSE(mean) against d_bag_labels [B]; Adam(lr) on d_w [N] (gradient zeroed where
+ * d_grad_mask [N] is 0, when use_mask) and on d_lin [F]; both clamped to [0,1].  Outputs of the LAST
+ * forward (taken before the last update, like the reference): d_best_dst / d_best_src int32 [B],
+ * d_diff [B] (prediction - label), d_src_val [N] (value of every source that was visited);
+ * d_loss_traj [epochs].  Gradient sums use integer atomics on 2^48-scaled values: deterministic. */
+int64_t mpgnn_score_bags_workspace_bytes(int64_t num_nodes, int64_t num_bags, int64_t feat);
+int mpgnn_score_bags(const mpgnn_graph* g, int64_t relation, const int32_t* d_bag_ptr, const int32_t* d_bag_src,
+                     int64_t num_bags, const float* d_bag_labels, const float* d_x, int64_t feat, float* d_w,
+                     float* d_lin, const uint8_t* d_grad_mask, int use_mask, int64_t epochs, double lr,
+                     float* d_loss_traj, int32_t* d_best_dst, int32_t* d_best_src, float* d_diff, float* d_src_val,
+                     void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- device-resident candidate trainer -------------------------------------------------
  * mpgnn_parallel_multiple (main.py:1117-1134) for ONE metapath: builds the MPNetm stack
  * (model.py:179-228: one conv per hop, relu + dropout, fc1, relu, fc2, log_softmax), then

@@ -42,6 +42,9 @@ PROTOTYPES = {
     "mpgnn_logsoftmax_nll": (_i32, [_ptr, _i64, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "mpgnn_macro_f1": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
     "mpgnn_adam_step": (_i32, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _ptr]),
+    "mpgnn_score_bags_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "mpgnn_score_bags": (_i32, [_ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i32, _i64, _dbl,
+                                _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "mpgnn_trainer_create": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _dbl,
                                     _u64, _u32, _i64, _c.POINTER(_ptr)]),
     "mpgnn_trainer_free": (None, [_ptr]),

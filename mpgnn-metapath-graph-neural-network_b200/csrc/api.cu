@@ -93,6 +93,11 @@ int score_relation(const mpgnn_graph_impl* g, int64_t rel, float* w, const float
                    float* m, float* v, float* loss_traj, int32_t* argmax_dst, void* ws_ptr, int64_t ws_bytes,
                    cudaStream_t s);
 
+int64_t score_bags_workspace_bytes(int64_t n, int64_t n_bags, int64_t feat);
+int score_bags(const mpgnn_graph_impl* g, int64_t rel, const int32_t* bag_ptr, const int32_t* bag_src, int64_t n_bags,
+               const float* bag_labels, const float* x, int64_t feat, float* w, float* lin, const uint8_t* grad_mask,
+               int use_mask, int64_t epochs, double lr, float* loss_traj, int32_t* best_dst, int32_t* best_src,
+               float* diff, float* src_val, void* ws_ptr, int64_t ws_bytes, cudaStream_t s);
 struct Trainer;
 int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int64_t hidden, int64_t classes,
                    const int64_t* h_rel, int64_t n_layers, const int64_t* train_idx, const int64_t* train_y,
@@ -324,6 +329,20 @@ int mpgnn_score_relation(const mpgnn_graph* g, int64_t relation, float* d_w, con
                          void* d_workspace, int64_t workspace_bytes, void* stream) {
   return score_relation(impl(g), relation, d_w, d_labels, d_source_mask, epochs, lr, d_m, d_v, d_loss_traj, d_argmax_dst, d_workspace,
                         workspace_bytes, stream_of(stream));
+}
+
+int64_t mpgnn_score_bags_workspace_bytes(int64_t num_nodes, int64_t num_bags, int64_t feat) {
+  return score_bags_workspace_bytes(num_nodes, num_bags, feat);
+}
+
+int mpgnn_score_bags(const mpgnn_graph* g, int64_t relation, const int32_t* d_bag_ptr, const int32_t* d_bag_src,
+                     int64_t num_bags, const float* d_bag_labels, const float* d_x, int64_t feat, float* d_w,
+                     float* d_lin, const uint8_t* d_grad_mask, int use_mask, int64_t epochs, double lr,
+                     float* d_loss_traj, int32_t* d_best_dst, int32_t* d_best_src, float* d_diff, float* d_src_val,
+                     void* d_workspace, int64_t workspace_bytes, void* stream) {
+  return score_bags(impl(g), relation, d_bag_ptr, d_bag_src, num_bags, d_bag_labels, d_x, feat, d_w, d_lin,
+                    d_grad_mask, use_mask, epochs, lr, d_loss_traj, d_best_dst, d_best_src, d_diff, d_src_val,
+                    d_workspace, workspace_bytes, stream_of(stream));
 }
 
 int mpgnn_trainer_create(const mpgnn_graph* g, const float* d_x, int64_t f_in, int64_t hidden, int64_t num_classes,

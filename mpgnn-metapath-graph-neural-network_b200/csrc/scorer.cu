@@ -174,3 +174,182 @@ int score_relation(const mpgnn_graph_impl* g, int64_t rel, float* w, const float
 }
 
 }  // namespace mpgnn
+
+// ============================================================================================
+// K5, bag mode (score_relation_bags_parallel / retrain_bags, main.py:814-917; OutputLayer.forward
+// BAGS branch, model.py:45-72).  A bag is a list of source nodes; its prediction is
+//   max over its sources s of  w[argmax_d (w[d] * a_s)] * a_s ,   a_s = <x[s], lin>
+// with first-maximum ties, `lin` the 1 x F LinearLayerAttri weight.  MSE(mean) against the bag
+// labels; Adam(lr) trains w (masked by grad_mask) and lin; both are clamped to [0,1].
+//   bag_fwd:    thread per bag   -> prediction, (destination, source) that produced it, diff;
+//               gradient contributions added as 2^48-scaled int64 (integer atomics are order
+//               independent, so the sums are deterministic without a per-epoch sort)
+//   bag_loss:   one block        -> loss[epoch]
+//   bag_update: thread per node / feature -> Adam + clamp, accumulators cleared
+// ============================================================================================
+namespace mpgnn {
+
+constexpr double kFix = 281474976710656.0;  // 2^48
+
+__global__ void __launch_bounds__(SC_THREADS) bag_fwd_kernel(
+    const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const int32_t* __restrict__ bag_ptr,
+    const int32_t* __restrict__ bag_src, int n_bags, const float* __restrict__ bag_labels,
+    const float* __restrict__ x, int feat, const float* __restrict__ lin, const float* __restrict__ w,
+    int32_t* __restrict__ best_dst, int32_t* __restrict__ best_src, float* __restrict__ diff,
+    float* __restrict__ src_val, long long* __restrict__ acc_w, long long* __restrict__ acc_lin,
+    float* __restrict__ partial) {
+  __shared__ float sh[SC_THREADS];
+  const int b = blockIdx.x * SC_THREADS + threadIdx.x;
+  float sq = 0.f;
+  if (b < n_bags) {
+    float cur = -10.f, cur_a = 0.f;
+    int32_t bd = -1, bs = -1;
+    float pred = 0.f;
+    for (int32_t q = bag_ptr[b]; q < bag_ptr[b + 1]; ++q) {
+      const int32_t s = bag_src[q];
+      float a = 0.f;
+      for (int f = 0; f < feat; ++f) a = fmaf(x[(int64_t)s * feat + f], lin[f], a);
+      const int32_t p0 = ptr[s], p1 = ptr[s + 1];
+      if (p1 <= p0) continue;                      // cleaned bags only hold sources with an edge
+      float best = w[idx[p0]] * a;
+      int32_t bp = p0;
+      for (int32_t p = p0 + 1; p < p1; ++p) {
+        const float v = w[idx[p]] * a;
+        if (v > best) {
+          best = v;
+          bp = p;
+        }
+      }
+      const float val = w[idx[bp]] * a;
+      src_val[s] = val;                            // same value from every bag that holds s
+      if (val > cur) {
+        cur = val;
+        cur_a = a;
+        pred = val;
+        bd = idx[bp];
+        bs = s;
+      }
+    }
+    const float d = pred - bag_labels[b];
+    best_dst[b] = bd;
+    best_src[b] = bs;
+    diff[b] = d;
+    sq = d * d;
+    if (bd >= 0) {
+      const double gi = 2.0 * (double)d / (double)n_bags;
+      atomicAdd(reinterpret_cast<unsigned long long*>(acc_w + bd),
+                (unsigned long long)(long long)llrint(gi * (double)cur_a * kFix));
+      const double wb = (double)w[bd];
+      for (int f = 0; f < feat; ++f)
+        atomicAdd(reinterpret_cast<unsigned long long*>(acc_lin + f),
+                  (unsigned long long)(long long)llrint(gi * wb * (double)x[(int64_t)bs * feat + f] * kFix));
+    }
+  }
+  sh[threadIdx.x] = sq;
+  __syncthreads();
+  for (int o = SC_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(SC_THREADS) bag_loss_kernel(const float* __restrict__ partial, int n_partial,
+                                                               int n_bags, float* __restrict__ loss_out) {
+  __shared__ float sh[SC_THREADS];
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n_partial; i += SC_THREADS) v += partial[i];
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = SC_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss_out = sh[0] / (float)n_bags;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) bag_update_kernel(
+    int64_t n, int feat, long long* __restrict__ acc_w, long long* __restrict__ acc_lin,
+    const uint8_t* __restrict__ grad_mask, int use_mask, float* __restrict__ w, float* __restrict__ lin,
+    float* __restrict__ m, float* __restrict__ v, float* __restrict__ ml, float* __restrict__ vl, float step_size,
+    float inv_sqrt_bc2, float one_minus_b1, float b2, float one_minus_b2, float eps) {
+  const int64_t j = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x;
+  if (j < n) {
+    float g = (float)((double)acc_w[j] / kFix);
+    acc_w[j] = 0;
+    if (use_mask && grad_mask[j] == 0) g = 0.f;          // frozen destinations (main.py:663-664)
+    const float mj = m[j] + (g - m[j]) * one_minus_b1;
+    const float vj = v[j] * b2 + one_minus_b2 * g * g;
+    m[j] = mj;
+    v[j] = vj;
+    const float wj = w[j] - step_size * (mj / (sqrtf(vj) * inv_sqrt_bc2 + eps));
+    w[j] = fminf(fmaxf(wj, 0.f), 1.f);
+  }
+  if (j < feat) {
+    const float g = (float)((double)acc_lin[j] / kFix);
+    acc_lin[j] = 0;
+    const float mj = ml[j] + (g - ml[j]) * one_minus_b1;
+    const float vj = vl[j] * b2 + one_minus_b2 * g * g;
+    ml[j] = mj;
+    vl[j] = vj;
+    const float lj = lin[j] - step_size * (mj / (sqrtf(vj) * inv_sqrt_bc2 + eps));
+    lin[j] = fminf(fmaxf(lj, 0.f), 1.f);                  // main.py:668
+  }
+}
+
+int64_t score_bags_workspace_bytes(int64_t n, int64_t n_bags, int64_t feat) {
+  const int64_t blocks = ceil_div(n_bags > 0 ? n_bags : 1, SC_THREADS);
+  return align_up(n * 8, 256) + align_up(feat * 8, 256) + align_up(n * 4, 256) * 2 + align_up(feat * 4, 256) * 2 +
+         align_up(blocks * 4, 256) + 256;
+}
+
+int score_bags(const mpgnn_graph_impl* g, int64_t rel, const int32_t* bag_ptr, const int32_t* bag_src, int64_t n_bags,
+               const float* bag_labels, const float* x, int64_t feat, float* w, float* lin, const uint8_t* grad_mask,
+               int use_mask, int64_t epochs, double lr, float* loss_traj, int32_t* best_dst, int32_t* best_src,
+               float* diff, float* src_val, void* ws_ptr, int64_t ws_bytes, cudaStream_t s) {
+  MPGNN_REQUIRE(g && bag_ptr && bag_src && bag_labels && x && w && lin && loss_traj && best_dst && best_src && diff &&
+                    src_val, MPGNN_EINVAL, "score_bags: NULL argument");
+  MPGNN_REQUIRE(rel >= 0 && rel < g->r, MPGNN_ERANGE, "score_bags: relation %lld outside [0,%lld)", (long long)rel,
+                (long long)g->r);
+  MPGNN_REQUIRE(n_bags >= 1 && feat >= 1 && feat <= SC_THREADS && epochs >= 1 && (!use_mask || grad_mask), MPGNN_EINVAL,
+                "score_bags: bad sizes");
+  const int64_t n = g->n;
+  const int blocks_b = (int)ceil_div(n_bags, SC_THREADS), blocks_n = (int)ceil_div(n, SC_THREADS);
+  Workspace ws(ws_ptr, ws_bytes);
+  long long* acc_w = ws.take<long long>(n);
+  long long* acc_lin = ws.take<long long>(feat);
+  float* m = ws.take<float>(n);
+  float* v = ws.take<float>(n);
+  float* ml = ws.take<float>(feat);
+  float* vl = ws.take<float>(feat);
+  float* partial = ws.take<float>(blocks_b);
+  MPGNN_REQUIRE(acc_w && acc_lin && m && v && ml && vl && partial, MPGNN_EINVAL, "score_bags: workspace too small");
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(acc_w, 0, (size_t)n * 8, s));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(acc_lin, 0, (size_t)feat * 8, s));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(m, 0, (size_t)n * 4, s));      // a fresh optimiser per restart (main.py:887)
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(v, 0, (size_t)n * 4, s));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(ml, 0, (size_t)feat * 4, s));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(vl, 0, (size_t)feat * 4, s));
+  const int32_t* ptr = g->csr_ptr + rel * n;
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  for (int64_t ep = 1; ep <= epochs; ++ep) {
+    bag_fwd_kernel<<<blocks_b, SC_THREADS, 0, s>>>(ptr, g->csr_idx, bag_ptr, bag_src, (int)n_bags, bag_labels, x,
+                                                  (int)feat, lin, w, best_dst, best_src, diff, src_val, acc_w, acc_lin,
+                                                  partial);
+    MPGNN_LAUNCH_CHECK();
+    bag_loss_kernel<<<1, SC_THREADS, 0, s>>>(partial, blocks_b, (int)n_bags, loss_traj + (ep - 1));
+    MPGNN_LAUNCH_CHECK();
+    if (ep == epochs) {
+      // the reference reads predictions / argmax maps of the LAST forward, i.e. before the last update:
+      // best_dst/best_src/diff/src_val are already final; the update below only moves w and lin
+    }
+    const double bc1 = 1.0 - pow(b1, (double)ep), bc2 = 1.0 - pow(b2, (double)ep);
+    bag_update_kernel<<<blocks_n, SC_THREADS, 0, s>>>(n, (int)feat, acc_w, acc_lin, grad_mask, use_mask, w, lin, m, v,
+                                                     ml, vl, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)),
+                                                     (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), (float)eps);
+    MPGNN_LAUNCH_CHECK();
+  }
+  return MPGNN_OK;
+}
+
+}  // namespace mpgnn

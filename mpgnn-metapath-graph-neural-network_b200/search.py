@@ -6,7 +6,9 @@ partition (main.py:1444-1450) and the final top-3 / greedy union (main.py:1463-1
 reference.  The mpi4py object collectives become one `torch.distributed.all_gather` of fixed-size
 records per step; every rank holds the whole graph and derives the (deterministic) decisions
 itself, so nothing else is exchanged.  The bag iterations (`for k in range(3)`, main.py:1381-1440)
-are not built yet: candidates are the length-1 metapaths kept by step 0.
+run the bag-mode K5 kernels (`mpgnn_score_bags`): restarts with freezing, acceptance rule, retrain,
+relabel and dictionary cleaning follow the reference; state that the reference ships between ranks
+as pickled dicts/models is recomputed locally (it is deterministic under the per-unit seeds).
 
 Randomness seam (the reference leaves Python's `random` unseeded, main.py:494): a relation is scored
 under `random.seed(SCORER_SEED_BASE + relation)`, a candidate is trained under
@@ -21,6 +23,9 @@ from . import _lib
 from .graph import RelationGraph, graph_for
 
 SCORER_SEED_BASE = 1000
+BAG_SEED_BASE = 2000           # bag-mode seam: seed = BAG_SEED_BASE + 100*len(metapath) + relation
+RETRAIN_SEED_SHIFT = 50        # retrain_bags of an accepted relation: seed + RETRAIN_SEED_SHIFT
+BAG_EPOCHS = 50                # main.py:890
 CANDIDATE_SEED = 30            # the reference's global torch.manual_seed (main.py:31-32)
 SCORER_EPOCHS = 100            # main.py:755
 SCORER_LR = 0.1                # main.py:522
@@ -35,10 +40,11 @@ def _np(t):
 
 def node_types_and_connected_relations(data_obj, BAGS, dataset):
     """main.py:56-84 -- candidate relations of a search step, in first-appearance edge order."""
-    if BAGS:
-        raise NotImplementedError("bag iterations of the search are not built yet (SURVEY §8 a18)")
     ei, et = _np(data_obj.edge_index), _np(data_obj.edge_type)
-    if dataset == "synthetic":
+    if BAGS:                                                          # main.py:58-67: rows inside any bag
+        nodes = np.array(sorted({v for b in data_obj.bags for v in b}), dtype=np.int64)
+        keep = np.isin(ei[0], nodes)
+    elif dataset == "synthetic":
         lab = _np(data_obj.labels).reshape(-1)
         keep = lab[ei[0]] == 1                                        # main.py:72
     else:
@@ -49,9 +55,10 @@ def node_types_and_connected_relations(data_obj, BAGS, dataset):
 
 
 def create_edge_dictionary(data, relation, source_nodes_mask, BAGS, dataset):
-    """main.py:387-425 (non-bag): ({src: [dst...]}, {dst: [label of each source...]})."""
+    """main.py:387-438: ({src: [dst...]}, {dst: [label of each source...]}); in bag mode the second
+    dictionary lists, per destination, the labels of all bags that contain each of its sources."""
     if BAGS:
-        raise NotImplementedError("bag mode is not built yet")
+        return _bag_dictionaries(data, relation, source_nodes_mask)
     ei = _np(data.edge_index)
     sel = _np(data.edge_type) == int(relation)
     rows, cols = ei[0][sel], ei[1][sel]
@@ -71,6 +78,77 @@ def create_edge_dictionary(data, relation, source_nodes_mask, BAGS, dataset):
         edge_dictionary[s].append(d)
         destination_dictionary.setdefault(d, []).append(l)
     return edge_dictionary, destination_dictionary
+
+
+def _bag_dictionaries(data, relation, source_nodes_mask):
+    ei = _np(data.edge_index)
+    sel = _np(data.edge_type) == int(relation)
+    rows, cols = ei[0][sel].tolist(), ei[1][sel].tolist()
+    in_mask = set(int(v) for v in source_nodes_mask)
+    present = set(rows)
+    edge_dictionary = {s: [] for s in source_nodes_mask if s in present}
+    tmp = {}
+    bag_labels = _np(data.bag_labels).reshape(-1).tolist()
+    for b, l in zip(data.bags, bag_labels):
+        for v in b:
+            tmp.setdefault(v, []).append(float(l))
+    destination_bag_dictionary = {}
+    for s, d in zip(rows, cols):
+        if s in in_mask:
+            edge_dictionary[s].append(d)
+        if s in tmp:
+            destination_bag_dictionary.setdefault(d, []).extend(tmp[s])
+    return edge_dictionary, destination_bag_dictionary
+
+
+def create_bags(edg_dictionary, dest_dictionary, data):
+    """main.py:545-572: per source, destinations whose every source label is > 0.9 form one positive
+    bag; every other destination is a singleton negative bag; duplicate bags are dropped."""
+    bag, labels, seen_single = [], [], set()
+    for key in edg_dictionary:
+        lst = []
+        for value in edg_dictionary[key]:
+            if min(dest_dictionary[value]) > 0.9:
+                lst.append(value)
+            elif value not in seen_single:
+                seen_single.add(value)
+                if [value] not in bag:
+                    bag.append([value])
+                    labels.append(0)
+        if lst:
+            bag.append(lst)
+            labels.append(1)
+    new_bag, new_labels, seen = [], [], set()
+    for b, l in zip(bag, labels):
+        t = tuple(b)
+        if t not in seen:
+            seen.add(t)
+            new_bag.append(b)
+            new_labels.append(l)
+    data.bags = new_bag
+    data.bag_labels = torch.tensor(new_labels, dtype=torch.float32).unsqueeze(-1)
+
+
+def clean_bags_for_relation_type(data, edge_dictionary):
+    """main.py:579-594."""
+    keep, keep_labels = [], []
+    labels = _np(data.bag_labels).reshape(-1).tolist()
+    for b, l in zip(data.bags, labels):
+        t = [v for v in b if v in edge_dictionary]
+        if t:
+            keep.append(t)
+            keep_labels.append(l)
+    return keep, torch.tensor(keep_labels, dtype=torch.float32).unsqueeze(-1)
+
+
+def reinitialize_weights(data, destination_dictionary, previous_weights, frozen, BAGS=False):
+    """main.py:499-516: frozen destinations keep their value, the others are re-drawn U(0,1)."""
+    weights = torch.zeros(int(data.num_nodes))
+    fz = set(frozen)
+    prev = previous_weights.reshape(-1)
+    for key in destination_dictionary:
+        weights[key] = prev[key] if key in fz else random.uniform(0.0, 1.0)
+    return weights
 
 
 def initialize_weights(data, destination_dictionary, BAGS):
@@ -134,6 +212,195 @@ def score_relation_parallel(data, relation, source_nodes, features_dim, dataset,
     graph = _graph_of(data, device)
     traj, _, _ = run_scorer(graph, relation, weights, node_labels, mask)
     return relation, float(traj[-1]), edge_dictionary, destination_dictionary
+
+
+class _ScoreModel:
+    """What the reference keeps of a trained `Score` module: the 1 x F LinearLayerAttri weight
+    (used by relabel_nodes_inside_bags / clean_dictionaries) and the trained destination weights."""
+
+    class _Out:
+        class _Lin:
+            def __init__(self, w):
+                self.weight = w
+
+        def __init__(self, w):
+            self.LinearLayerAttri = _ScoreModel._Out._Lin(w)
+
+    def __init__(self, lin, weights):
+        self.output = _ScoreModel._Out(lin.reshape(1, -1).clone())
+        self.weights = weights
+
+
+def bag_seed(metapath_len, relation):
+    return BAG_SEED_BASE + 100 * int(metapath_len) + int(relation)
+
+
+def _ragged_i32(lists, device):
+    flat = torch.tensor([v for l in lists for v in l], dtype=torch.int32, device=device)
+    ptr = torch.tensor(np.cumsum([0] + [len(l) for l in lists]), dtype=torch.int32, device=device)
+    return flat, ptr
+
+
+def run_bag_restart(graph, relation, bags, bag_labels, x_dev, weights, lin, grad_mask, use_mask, epochs=BAG_EPOCHS,
+                    lr=SCORER_LR):
+    """One restart (`epochs` bag-mode train() steps) on the device.  Returns host copies of the loss
+    trajectory, final weights, final linear weight, and the last forward's per-bag destination /
+    squared error and per-source values."""
+    lib = _lib.load()
+    dev = graph.device
+    n, feat = graph.num_nodes, x_dev.size(1)
+    src, ptr = _ragged_i32(bags, dev)
+    lab = bag_labels.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+    w = weights.to(device=dev, dtype=torch.float32).contiguous().clone()
+    ln = lin.to(device=dev, dtype=torch.float32).contiguous().clone()
+    gm = grad_mask.to(device=dev, dtype=torch.uint8).contiguous()
+    nb = len(bags)
+    traj = torch.empty(epochs, device=dev)
+    best_dst = torch.empty(nb, dtype=torch.int32, device=dev)
+    best_src = torch.empty(nb, dtype=torch.int32, device=dev)
+    diff = torch.empty(nb, device=dev)
+    src_val = torch.full((n,), float("nan"), device=dev)
+    ws = torch.empty(lib.mpgnn_score_bags_workspace_bytes(n, nb, feat), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mpgnn_score_bags(graph.handle, int(relation), _lib.ptr(ptr), _lib.ptr(src), nb, _lib.ptr(lab),
+                                        _lib.ptr(x_dev), feat, _lib.ptr(w), _lib.ptr(ln), _lib.ptr(gm), int(use_mask),
+                                        int(epochs), float(lr), _lib.ptr(traj), _lib.ptr(best_dst), _lib.ptr(best_src),
+                                        _lib.ptr(diff), _lib.ptr(src_val), _lib.ptr(ws), ws.numel(),
+                                        _lib.current_stream()))
+    return traj.cpu(), w.cpu(), ln.cpu(), best_dst.cpu(), (diff.cpu() ** 2), src_val.cpu()
+
+
+def _bag_sources(bags):
+    mask, seen = [], set()
+    for b in bags:
+        for v in b:
+            if v not in seen:
+                seen.add(v)
+                mask.append(v)
+    return mask
+
+
+def _bag_restart_loop(data, relation, features_dim, seed, max_restarts=None, device=None, record=None):
+    """Shared body of score_relation_bags_parallel (restarts until two non-improvements, freezing)
+    and retrain_bags (exactly one restart, no freezing)."""
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    random.seed(seed)
+    torch.manual_seed(seed)
+    source_nodes_mask = _bag_sources(data.bags)
+    edge_dictionary, destination_dictionary = create_edge_dictionary(data, relation, source_nodes_mask, BAGS=True,
+                                                                     dataset=None)
+    bags, bag_labels = clean_bags_for_relation_type(data, edge_dictionary)
+    weights = initialize_weights(data, destination_dictionary, BAGS=True)
+    n = int(data.num_nodes)
+    grad_mask = torch.ones(n, dtype=torch.uint8)
+    labels_list = bag_labels.reshape(-1).tolist()
+    v = len(bags) == 1 or (len(bags) > 1 and labels_list.count(1) == 0)
+    graph = _graph_of(data, device)
+    x_dev = data.x.to(device=device, dtype=torch.float32).contiguous()
+    predictions_for_each_restart, frozen = {}, []
+    rest, current_loss, restarts, lin = 0, 100.0, 0, None
+    trained_w = weights
+    while rest < 2 and len(bags) > 0:
+        lin0 = torch.nn.Linear(int(features_dim), 1, bias=False).weight.detach()[0].clone()   # Score.__init__
+        traj, trained_w, lin, best_dst, loss_per_bag, src_val = run_bag_restart(
+            graph, relation, bags, bag_labels, x_dev, weights, lin0, grad_mask, bool(frozen))
+        loss = float(traj[-1])
+        if record is not None:
+            record.setdefault("traj", []).extend(traj.tolist())
+            record.setdefault("lin", []).append(lin.numpy().copy())
+        visited = set()
+        for b in bags:                                                   # dict order of the reference's forward
+            for s_ in b:
+                if s_ not in visited:
+                    visited.add(s_)
+                    predictions_for_each_restart.setdefault(s_, []).append(float(src_val[s_]))
+        restarts += 1
+        if max_restarts is not None:                                     # retrain_bags: one restart, nothing frozen
+            frozen = []
+            weights = reinitialize_weights(data, destination_dictionary, trained_w, frozen)
+            if restarts >= max_restarts:
+                break
+            continue
+        if loss < current_loss:
+            arg = {}
+            for i, b in enumerate(bags):                                 # keyed by str(bag): later duplicates overwrite
+                arg[tuple(b)] = int(best_dst[i])
+            frozen = []
+            for idx, dst in enumerate(arg.values()):                     # retrieve_destinations_low_loss (:530-543)
+                if float(loss_per_bag[idx]) < 0.0001 and dst not in frozen:
+                    frozen.append(dst)
+            current_loss, rest = loss, 0
+        else:
+            rest += 1
+        for node in frozen:
+            grad_mask[node] = 0
+        weights = reinitialize_weights(data, destination_dictionary, trained_w, frozen)
+    if record is not None:
+        record.update(bags=bags, bag_labels=labels_list, dest_keys=list(destination_dictionary.keys()))
+    model = _ScoreModel(lin if lin is not None else torch.zeros(int(features_dim)), trained_w)
+    return current_loss, model, predictions_for_each_restart, v
+
+
+def score_relation_bags_parallel(data_object, relation, features_dim, dataset, metapath_len=1, device=None, record=None):
+    """main.py:853-917 -> (relation, best loss, model, predictions_for_each_restart, skip flag)."""
+    loss, model, preds, v = _bag_restart_loop(data_object, int(relation), features_dim,
+                                              bag_seed(metapath_len, relation), device=device, record=record)
+    return int(relation), loss, model, preds, v
+
+
+def retrain_bags(data, relation, best_pred_for_each_restart, BAGS, features_dim, dataset, metapath_len=1, device=None):
+    """main.py:814-850: one more restart of 50 epochs; its per-source values are appended to the
+    predictions collected while scoring."""
+    _, _, preds, _ = _bag_restart_loop(data, int(relation), features_dim,
+                                       bag_seed(metapath_len, relation) + RETRAIN_SEED_SHIFT, max_restarts=1,
+                                       device=device)
+    for key, vals in preds.items():
+        best_pred_for_each_restart.setdefault(key, []).extend(vals)
+    return best_pred_for_each_restart
+
+
+def relabel_nodes_inside_bags(predictions_for_each_restart, data, mod):
+    """main.py:596-634: a node inside the bags becomes positive iff any restart predicted > 0.9."""
+    new_labels = torch.zeros(int(data.num_nodes), 1)
+    for k, v in predictions_for_each_restart.items():
+        if max(v) > 0.9:
+            new_labels[k] = 1
+    data.labels = new_labels.clone()
+    return list(predictions_for_each_restart.keys()), new_labels
+
+
+def clean_dictionaries(data, edg_dict, dest_dict, mod):
+    """main.py:456-477: drop sources whose feature . LinearLayerAttri weight is < 0.01 (and one 0
+    label from each of their destinations)."""
+    edge_copy, dest_copy = edg_dict.copy(), dest_dict.copy()
+    lin = mod.output.LinearLayerAttri.weight[0]
+    x = data.x.to(torch.float32)
+    for key in edg_dict:
+        if torch.dot(x[key].cpu(), lin.cpu()).item() < 0.01:
+            for destination in edge_copy[key]:
+                if 0 in dest_copy[destination]:
+                    dest_copy[destination].remove(0)
+            del edge_copy[key]
+    return edge_copy, dest_copy
+
+
+def accept_bag_relations(final_result):
+    """main.py:1410-1424: accept relations with loss < the value at the largest gap when there are
+    more than two gaps, everything with zero or one gap, and NOTHING with exactly two gaps."""
+    arr = sorted(l for _, l in final_result)
+    diffs = np.diff(arr)
+    if len(diffs) > 2:
+        cut = arr[int(np.argmax(diffs))]
+        return [r for r, l in final_result if l < cut]
+    if len(diffs) in (0, 1):
+        return [r for r, _ in final_result]
+    return []
+
+
+def _copy_bag(data):
+    new = type(data).__new__(type(data))
+    new.__dict__.update({k: v for k, v in data.__dict__.items() if k != "_b200_staged"})
+    return new
 
 
 def _mask_of(nodes, n):
@@ -218,14 +485,21 @@ def final_selection(final_dict, train_union_fn):
 
 
 def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, dataset, comm=None,
-                  score_fn=None, eval_fn=None, union_fn=None, log=None):
-    """main.py:1289-1476 without the bag iterations.  `score_fn(data, rel)` -> loss,
+                  score_fn=None, eval_fn=None, union_fn=None, bag_score_fn=None, log=None, max_depth=3):
+    """main.py:1289-1476.  `score_fn(data, rel)` -> (loss, edge_dict, dest_dict) or a bare loss,
+    `bag_score_fn(bag_data, rel, metapath_len)` -> (rel, loss, model, predictions, skip),
     `eval_fn(meta)` -> validation macro-F1, `union_fn(metas)` -> test macro-F1 default to the device
-    implementations; tests inject CPU stand-ins to exercise the fan-out and the rules."""
+    implementations; tests inject CPU stand-ins to exercise the fan-out and the rules.
+    `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381)."""
     from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_x
     comm = comm or Comm()
     if score_fn is None:
-        score_fn = lambda d, rel: score_relation_parallel(d, rel, d.source_nodes_mask, input_dim, dataset)[1]  # noqa: E731
+        def score_fn(d, rel):
+            r = score_relation_parallel(d, rel, d.source_nodes_mask, input_dim, dataset)
+            return r[1], r[2], r[3]
+    if bag_score_fn is None:
+        def bag_score_fn(bag_data, rel, mlen):
+            return score_relation_bags_parallel(bag_data, rel, input_dim, dataset, metapath_len=mlen)
     if eval_fn is None:
         def eval_fn(meta):
             torch.manual_seed(CANDIDATE_SEED)
@@ -238,17 +512,83 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     # ---- step 0: every rank scores its share of the relations (main.py:1319-1328) ----------
     actual_relations = node_types_and_connected_relations(data, BAGS=False, dataset=dataset)
     local = relation_split(actual_relations, comm.size, comm.rank)
-    mine = [[float(rel), float(score_fn(data, rel))] for rel in local]
+    local_out = {}
+    mine = []
+    for rel in local:
+        out = score_fn(data, rel)
+        loss = out[0] if isinstance(out, tuple) else out
+        local_out[rel] = out
+        mine.append([float(rel), float(loss)])
     gathered = comm.allgather_records(mine, 2, max(1, len(actual_relations)))
     final_result = [(int(r), l) for part in gathered for r, l in part]      # sum(result, []) in rank order
     best = gap_select_step0([r for r, _ in final_result], [l for _, l in final_result])
-    final_metapaths_list = [[r] for r in best]
+    step0 = {"relations": [r for r, _ in final_result], "losses": [l for _, l in final_result], "kept": best}
     if log:
-        log("step 0: relations %s losses %s kept %s" % ([r for r, _ in final_result],
-                                                       ["%.5f" % l for _, l in final_result], best))
+        log("step 0: relations %s losses %s kept %s" % (step0["relations"], ["%.5f" % l for l in step0["losses"]], best))
+    current_metapaths_list = [[r] for r in best]
+    final_metapaths_list = [list(m) for m in current_metapaths_list]
+    intermediate = [list(m) for m in current_metapaths_list]
+    steps = []
+    if max_depth > 0 and current_metapaths_list:
+        # per-metapath state the reference keeps in current_metapaths_dict: edge dict, dest dict, data copy
+        state = {}
+        for rel in best:
+            out = local_out.get(rel)
+            if not isinstance(out, tuple):                       # scored on another rank: recompute locally
+                out = score_fn(data, rel)                        # (deterministic under the per-relation seed)
+            if not isinstance(out, tuple):
+                state = None                                     # stand-in scorer without dictionaries: no bag steps
+                break
+            state[str([rel])] = [out[1], out[2], _copy_bag(data)]
+        for k in range(max_depth if state is not None else 0):
+            for meta in list(current_metapaths_list):
+                edg, dst, bag_data = state[str(meta)]
+                create_bags(edg, dst, bag_data)                                           # main.py:1385
+                rels_k = node_types_and_connected_relations(bag_data, BAGS=True, dataset=dataset)
+                final_metapaths_list.append(list(meta))                                   # main.py:1388 (duplicates)
+                intermediate.remove(meta)
+                if not rels_k:
+                    continue
+                local_k = relation_split(rels_k, comm.size, comm.rank)
+                cache, mine = {}, []
+                for rel in local_k:
+                    res = bag_score_fn(bag_data, rel, len(meta))
+                    cache[rel] = res
+                    if not res[4]:                                                        # skip flag (main.py:1405)
+                        mine.append([float(rel), float(res[1])])
+                gathered = comm.allgather_records(mine, 2, max(1, len(rels_k)))
+                result_k = [(int(r), l) for part in gathered for r, l in part]
+                accepted = accept_bag_relations(result_k)
+                steps.append({"metapath": list(meta), "relations": [r for r, _ in result_k],
+                              "losses": [l for _, l in result_k], "accepted": accepted})
+                if log:
+                    log("depth %d meta %s: relations %s losses %s accepted %s" % (
+                        k + 1, meta, steps[-1]["relations"], ["%.5f" % l for l in steps[-1]["losses"]], accepted))
+                for rel, loss in result_k:
+                    if rel not in accepted:
+                        continue
+                    tmp_meta = [rel] + list(meta)
+                    intermediate.append(tmp_meta)
+                    if tmp_meta not in final_metapaths_list:
+                        final_metapaths_list.append(tmp_meta)
+                    res = cache.get(rel) or bag_score_fn(bag_data, rel, len(meta))        # other rank's relation
+                    data_copy = _copy_bag(bag_data)
+                    preds = {kk: list(vv) for kk, vv in res[3].items()}
+                    preds = retrain_bags(data_copy, rel, preds, True, input_dim, dataset, metapath_len=len(meta))
+                    src_mask, _ = relabel_nodes_inside_bags(preds, data_copy, res[2])
+                    e2, d2 = create_edge_dictionary(data_copy, rel, src_mask, BAGS=False, dataset="synthetic")
+                    e2, d2 = clean_dictionaries(data_copy, e2, d2, res[2])
+                    state[str(tmp_meta)] = [e2, d2, data_copy]
+            current_metapaths_list = [list(m) for m in intermediate]
     # ---- evaluation: contiguous candidate blocks (main.py:1444-1462) -------------------------
     lo, hi = candidate_block(len(final_metapaths_list), comm.size, comm.rank)
-    mine = [[float(i), float(eval_fn(final_metapaths_list[i]))] for i in range(lo, hi)]
+    done = {}
+    mine = []
+    for i in range(lo, hi):
+        key = str(final_metapaths_list[i])
+        if key not in done:                       # duplicates (main.py:1388) train to the same number under the seam
+            done[key] = float(eval_fn(final_metapaths_list[i]))
+        mine.append([float(i), done[key]])
     gathered = comm.allgather_records(mine, 2, max(1, len(final_metapaths_list)))
     final_dict = {}
     for part in gathered:                                                    # rank order; later keys overwrite
@@ -258,5 +598,5 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     f_meta, test_f1 = final_selection(final_dict, union_fn)
     if log:
         log("final meta: %s test acc: %s" % (f_meta, test_f1))
-    return {"relations": [r for r, _ in final_result], "losses": [l for _, l in final_result], "kept": best,
-            "final_dict": final_dict, "final_meta": f_meta, "test_f1": test_f1}
+    return {"relations": step0["relations"], "losses": step0["losses"], "kept": best, "bag_steps": steps,
+            "candidates": final_metapaths_list, "final_dict": final_dict, "final_meta": f_meta, "test_f1": test_f1}

@@ -1,0 +1,69 @@
+"""GPU parity of the bag iterations of the search (K5 bag mode) against the reference goldens
+(tests/golden/search_bags_len3.npz) and the behavioural anchor of SURVEY §8c: on the fixture the
+greedy search must recover the ground-truth metapath [1, 0]."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import search_oracle as so
+
+import mpgnn_b200
+from mpgnn_b200 import search
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1500, method="thread")]
+
+
+def _data(fx):
+    return mpgnn_b200.Data(x=fx["x"], edge_index=fx["edge_index"], edge_type=fx["edge_type"],
+                           labels=fx["labels"].unsqueeze(-1), num_nodes=fx["x"].size(0), source_nodes_mask=[])
+
+
+def _unragged(flat, ptr):
+    return [flat[ptr[i]:ptr[i + 1]].tolist() for i in range(len(ptr) - 1)]
+
+
+@pytest.mark.parametrize("rel0", [0, 1])
+def test_bag_scorer_matches_reference_golden(fx3, rel0):
+    g = load_golden("search_bags_len3")
+    data = _data(fx3)
+    _, _, ed, dd = mpgnn_b200.score_relation_parallel(data, rel0, [], 2, "synthetic")
+    bag_data = search._copy_bag(data)
+    search.create_bags(ed, dd, bag_data)
+    pre = "m%d_" % rel0
+    assert bag_data.bags == _unragged(g[pre + "bags_flat"], g[pre + "bags_ptr"])          # bit-exact bag construction
+    assert bag_data.bag_labels.reshape(-1).tolist() == g[pre + "bag_labels"].tolist()
+    rels = search.node_types_and_connected_relations(bag_data, BAGS=True, dataset="synthetic")
+    assert rels == g[pre + "relations"].tolist()
+    for rr in rels:
+        tag = pre + "r%d_" % rr
+        rec = {}
+        rel, loss, model, preds, skip = search.score_relation_bags_parallel(bag_data, rr, 2, "synthetic", metapath_len=1,
+                                                                            record=rec)
+        assert rec["bags"] == _unragged(g[tag + "bags_flat"], g[tag + "bags_ptr"])
+        assert rec["dest_keys"] == g[tag + "dest_keys"].tolist()
+        assert bool(skip) == bool(g[tag + "skip"])
+        ref = g[tag + "loss_traj"]
+        got = np.array(rec["traj"])
+        # first restart: same initial weights (same RNG seam), so the trajectory must agree closely
+        assert np.allclose(got[:50], ref[:50], rtol=2e-3, atol=1e-6), (got[:5], ref[:5])
+        assert abs(loss - float(g[tag + "loss"])) <= max(2e-4, 0.05 * float(g[tag + "loss"]))
+        assert list(preds.keys()) == g[tag + "pred_keys"].tolist()
+
+
+def test_greedy_search_recovers_ground_truth_metapath(fx3):
+    data = _data(fx3)
+    bag = mpgnn_b200.Data(**{k: fx3[k] for k in ("x", "edge_index", "edge_type", "train_idx", "train_y", "val_idx",
+                                                  "val_y", "test_idx", "test_y")}, num_nodes=fx3["x"].size(0))
+    from mpgnn_b200 import main as m
+    ev = lambda meta: (torch.manual_seed(30), m.mpgnn_parallel_multiple(bag, 2, 64, 4, 64, 2, [meta], epochs=300))[1]  # noqa: E731
+    un = lambda metas: (torch.manual_seed(30), m.mpgnn_parallel_multiple_x(bag, 2, 64, 4, 64, 2, metas, True,  # noqa: E731
+                                                                           epochs=300))[1]
+    logs = []
+    res = search.greedy_search(data, bag, 2, 64, 4, 64, 2, "synthetic", eval_fn=ev, union_fn=un, log=logs.append,
+                               max_depth=1)
+    print("\n".join(logs))
+    assert res["kept"] == [0, 1]
+    assert [1, 0] in res["candidates"]                       # the generator's ground truth (metapath.dat: "1 0")
+    assert res["final_dict"]["[1, 0]"] > 0.99
+    assert res["final_meta"][0] == [1, 0] and res["test_f1"] > 0.99

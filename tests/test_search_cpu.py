@@ -55,8 +55,25 @@ def test_host_dictionaries_and_relations_match_oracle(fx3):
         random.seed(search.SCORER_SEED_BASE + r)
         w = search.initialize_weights(data, dd, BAGS=False)
         assert np.allclose(w[torch.tensor(list(dd.keys()))].numpy(), g["r%d_init_w" % r], atol=0)
-    with pytest.raises(NotImplementedError):
-        search.node_types_and_connected_relations(data, BAGS=True, dataset="synthetic")
+    # bag-mode host functions against the oracle restatement
+    ei, et, lab = fx3["edge_index"].numpy(), fx3["edge_type"].numpy(), fx3["labels"].numpy()
+    ed, dd = so.relation_dictionaries(ei, et, 0, lab)
+    bags_o, labels_o = so.create_bags(ed, dd)
+    d2 = _data(fx3)
+    search.create_bags(ed, dd, d2)
+    assert d2.bags == bags_o and d2.bag_labels.reshape(-1).tolist() == [float(v) for v in labels_o]
+    assert search.node_types_and_connected_relations(d2, BAGS=True, dataset="synthetic") == \
+        so.connected_relations_bags(ei, et, bags_o)
+    mask, ed_b, dd_b = so.bag_dictionaries(ei, et, 1, bags_o, labels_o)
+    assert mask == search._bag_sources(d2.bags)
+    e_p, d_p = search.create_edge_dictionary(d2, 1, mask, BAGS=True, dataset="synthetic")
+    assert e_p == ed_b and d_p == dd_b and list(d_p) == list(dd_b) and list(e_p) == list(ed_b)
+    kb, kl = so.clean_bags_for_relation_type(bags_o, labels_o, ed_b)
+    kb2, kl2 = search.clean_bags_for_relation_type(d2, e_p)
+    assert kb == kb2 and kl2.reshape(-1).tolist() == kl
+    assert search.accept_bag_relations([(1, 0.1), (2, 0.2)]) == [1, 2]
+    assert search.accept_bag_relations([(1, 0.1), (2, 0.2), (3, 0.9)]) == []          # exactly two gaps: nothing
+    assert search.accept_bag_relations([(1, 0.1), (2, 0.2), (3, 0.9), (4, 0.95)]) == [1]   # strict `<`
 
 
 def test_selection_rules_and_partitions():
@@ -139,3 +156,32 @@ def test_fanout_world_size_2_gloo_matches_single_process():
         assert p.exitcode == 0
     for r in range(2):           # every rank derives the same decisions as the single-process run
         assert results[r] == single
+
+
+def test_oracle_bag_scorer_matches_reference_golden(fx3):
+    """Bag mode (restarts, freezing, LinearLayerAttri training) of the oracle against the trajectory
+    recorded from the unmodified reference (tests/golden/make_golden_bags.py)."""
+    g = load_golden("search_bags_len3")
+    ei, et, lab = fx3["edge_index"].numpy(), fx3["edge_type"].numpy(), fx3["labels"].numpy()
+
+    def unr(f, p):
+        return [f[p[i]:p[i + 1]].tolist() for i in range(len(p) - 1)]
+
+    ed, dd = so.relation_dictionaries(ei, et, 0, lab)
+    bags, labels = so.create_bags(ed, dd)
+    assert bags == unr(g["m0_bags_flat"], g["m0_bags_ptr"]) and labels == g["m0_bag_labels"].tolist()
+    assert so.connected_relations_bags(ei, et, bags) == g["m0_relations"].tolist()
+    rec = {}
+    loss, preds, skip, lin = so.score_relation_bags(ei, et, 1, fx3["x"], fx3["x"].size(0), bags, labels,
+                                                    so.bag_seed(1, 1), record=rec)
+    tag = "m0_r1_"
+    ref = g[tag + "loss_traj"]
+    assert len(rec["traj"]) == len(ref) and np.allclose(rec["traj"], ref, rtol=1e-4, atol=1e-7)
+    assert loss == pytest.approx(float(g[tag + "loss"]), abs=1e-7) and bool(skip) == bool(g[tag + "skip"])
+    assert rec["dest_keys"] == g[tag + "dest_keys"].tolist()
+    assert rec["bags"] == unr(g[tag + "bags_flat"], g[tag + "bags_ptr"])
+    assert rec["frozen_hist"] == unr(g[tag + "frozen_flat"], g[tag + "frozen_ptr"])
+    assert np.allclose(np.array(rec["lin_hist"]), g[tag + "lin_hist"], atol=1e-6)
+    assert list(preds.keys()) == g[tag + "pred_keys"].tolist()
+    vals = np.array([x for k in preds for x in preds[k]])
+    assert np.allclose(vals, g[tag + "pred_vals"], atol=1e-5)
