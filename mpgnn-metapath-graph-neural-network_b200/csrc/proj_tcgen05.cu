@@ -11,11 +11,14 @@
 //  * a CTA owns ONE column slice of BN outputs (BN*K*8 bytes of B, hi+lo, resident in shared
 //    memory for the whole kernel) and walks 128-row tiles; the CTAs owning the other slices of a
 //    row tile run next to it, so the second read of the A tile is an L2 hit.
-//  * 16 producer warps stream A: 128-bit global loads issued 4 K-chunks ahead (register prefetch
-//    hides HBM latency), hi/lo split, conflict-free stores into a 2-stage ring of K-major
-//    no-swizzle UMMA tiles; generic->async proxy fence; one mbarrier arrive per warp.
-//  * one warp issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step) from an
-//    elected lane into one of two TMEM accumulators and tcgen05.commit's the barriers.
+//  * the A operand is fed to the MMA from TENSOR MEMORY, not shared memory: with three MMAs per
+//    K-step the shared-memory operand fetch (A 4 KB + B 2-4 KB per MMA at ~110 B/clk) was the
+//    bound, so only the small resident B is read from shared memory now.  16 producer warps
+//    stream A with coalesced 128-bit global loads, transpose it through a padded shared tile so
+//    that every thread owns 8 consecutive K values of ONE row, split hi/lo in registers and
+//    tcgen05.st them into a 2-stage ring of TMEM columns (lane = row, column = k).
+//  * one warp issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step, A from TMEM) from
+//    an elected lane into one of two TMEM accumulators and tcgen05.commit's the barriers.
 //  * 8 epilogue warps (two per TMEM lane quarter, each owning alternate 32-column chunks)
 //    tcgen05.ld the accumulator, apply bias / degree normalisation / relu / dropout in
 //    registers, transpose through a padded shared staging tile and write 64-byte row segments.
@@ -29,8 +32,9 @@ namespace tc {
 
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                       // fp32 elements per pipeline stage (4 MMA K-steps)
-constexpr int kStages = 2;
-constexpr int kPrefetch = 4;                      // chunks in flight in producer registers
+constexpr int kStages = 4;                        // TMEM A stages in flight (64 columns each)
+constexpr int kTransTiles = 2;                    // shared transpose tiles (only live between STS and LDS)
+constexpr int kPrefetch = 2;                      // chunks in flight in producer registers
 constexpr int kProducerWarps = 16;
 constexpr int kEpiWarps = 8;
 // Warp roles by warp id: producers first, epilogue warps next (id % 4 = TMEM lane quarter;
@@ -38,7 +42,9 @@ constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = kProducerWarps + kEpiWarps;              // 24
 constexpr int kThreads = (kMmaWarp + 1) * 32;                     // 800
 constexpr int kProducerThreads = kProducerWarps * 32;             // 512
-constexpr int kStageBytes = kTileM * kChunkK * 4;                 // 16 KB per hi or lo
+constexpr int kTransLd = kChunkK + 4;                              // padded transpose-tile row (floats)
+constexpr int kTransBytes = kTileM * kTransLd * 4;                // 18 KB per transpose tile
+constexpr int kACols = 2 * kChunkK;                               // TMEM columns per A stage: hi | lo
 constexpr int kEpiCols = 32;                                      // columns per tcgen05.ld
 constexpr int kStgCols = 16;                                      // columns per staging pass
 constexpr int kStgLd = kStgCols + 4;                              // padded staging row (floats)
@@ -80,8 +86,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   const int b_bytes = K * BN * 4;                         // one of hi / lo
   uint8_t* sm_b_hi = smem;
   uint8_t* sm_b_lo = smem + b_bytes;
-  uint8_t* sm_a = smem + 2 * b_bytes;                     // kStages x {hi, lo}
-  float* sm_stg = reinterpret_cast<float*>(sm_a + kStages * 2 * kStageBytes);   // kEpiWarps x 32 x kStgLd
+  uint8_t* sm_t = smem + 2 * b_bytes;                     // kStages transpose tiles [128][kTransLd] fp32
+  float* sm_stg = reinterpret_cast<float*>(sm_t + kTransTiles * kTransBytes);       // kEpiWarps x 32 x kStgLd
   float* sm_bias = sm_stg + kEpiWarps * 32 * kStgLd;                            // BN floats (slice bias)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_bias + 128);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
@@ -110,8 +116,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp) {  // TMEM: two fp32 accumulators of BN columns
-    const uint32_t ncols = 2 * BN;
+  if (warp == kMmaWarp) {  // TMEM: two fp32 accumulators of BN columns + kStages A stages (hi|lo)
+    const uint32_t ncols = 512;
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(ncols)
                  : "memory");
@@ -129,12 +135,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + (uint32_t)(2 * BN);   // A stages live after the two accumulators
 
   if (warp < kProducerWarps) {
     // ================================ A producers =======================================
-    // two 16-byte units per thread and chunk; lane -> (row-in-core r, k-core c4) keeps the
-    // shared-memory stores conflict free and the global loads sector aligned
-    int u_row[2], u_koff[2], u_soff[2];
+    // load side: two 16-byte units per thread and chunk, lane -> (row-in-8-group r, 16-byte column c4):
+    // 64-byte global segments, conflict-free stores into the transpose tile (row pitch 144 B).
+    // TMEM side: warp w owns lane quarter w&3 (rows 32*(w&3)+lane) and the 8 K-columns (w>>2)*8...
+    int u_row[2], u_koff[2], u_toff[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int idx = tid + kProducerThreads * u;   // 0..1023
@@ -142,8 +150,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       u_row[u] = (q & 15) * 8 + r;
       const int core = (q >> 4) * 4 + c4;
       u_koff[u] = core * 4;
-      u_soff[u] = (u_row[u] >> 3) * ((kChunkK / 4) * 128) + core * 128 + (u_row[u] & 7) * 16;
+      u_toff[u] = u_row[u] * (kTransLd * 4) + core * 16;
     }
+    const int quarter = warp & 3, colgrp = warp >> 2;
+    const int my_toff = (quarter * 32 + lane) * (kTransLd * 4) + colgrp * 32;
+    const uint32_t my_taddr = tmem_a + (uint32_t)(colgrp * 8) + ((uint32_t)(quarter * 32) << 16);
     const int total = my_tiles * kch;
     float4 buf[kPrefetch][2];
     // prefetch cursor (tile, chunk) advanced incrementally: no 64-bit div/mod in the loop
@@ -163,17 +174,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       }
       if (++pf_c == kch) { pf_c = 0; ++pf_tile; }
     };
-    auto store = [&](int s, const float4 (&src)[2]) {
-      uint8_t* hi_base = sm_a + (size_t)s * 2 * kStageBytes;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float4 v = src[u];
-        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        *reinterpret_cast<float4*>(hi_base + u_soff[u]) = h;
-        *reinterpret_cast<float4*>(hi_base + kStageBytes + u_soff[u]) = l;
-      }
-    };
 #pragma unroll
     for (int j = 0; j < kPrefetch; ++j)
       if (j < total) issue(buf[j]);
@@ -184,12 +184,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       for (int j = 0; j < kPrefetch; ++j) {
         const int it = it0 + j;
         if (it < total) {
+          uint8_t* tile = sm_t + (size_t)(it & (kTransTiles - 1)) * kTransBytes;
+          // (1) raw fp32 chunk -> transpose tile.  This tile was last read two chunks ago; the
+          //     named barrier of the previous chunk ordered those reads before these writes.
+          *reinterpret_cast<float4*>(tile + u_toff[0]) = buf[j][0];
+          *reinterpret_cast<float4*>(tile + u_toff[1]) = buf[j][1];
+          asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+          if (it + kPrefetch < total) issue(buf[j]);
+          // (2) my row slice: 8 consecutive K values of one row -> hi/lo split in registers
+          const float4 v0 = *reinterpret_cast<const float4*>(tile + my_toff);
+          const float4 v1 = *reinterpret_cast<const float4*>(tile + my_toff + 16);
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float h = tf32_hi(vv[e]);
+            hi[e] = __float_as_uint(h);
+            lo[e] = __float_as_uint(vv[e] - h);
+          }
+          // (3) TMEM stage s (hi columns [0,32), lo columns [32,64)) once the MMAs that read it are done
           mbar_wait(bar_empty + 8 * s, sph ^ 1u);
-          store(s, buf[j]);
-          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t ta = my_taddr + (uint32_t)(s * kACols);
+          tmem_st8(ta, hi);
+          tmem_st8(ta + kChunkK, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full + 8 * s);
-          if (it + kPrefetch < total) issue(buf[j]);
           if (++s == kStages) { s = 0; sph ^= 1u; }
         }
       }
@@ -271,8 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   } else {
     // ================================ MMA issuer (whole warp converged; one elected lane issues) ====
     const uint32_t idesc = make_idesc(kTileM, BN);
-    const uint32_t a_sbo = (kChunkK / 4) * 128, b_sbo = (uint32_t)(K / 4) * 128;
-    const uint32_t a_lo0 = desc_lo(smem_u32(sm_a));
+    const uint32_t b_sbo = (uint32_t)(K / 4) * 128;
     const uint32_t bh_lo0 = desc_lo(smem_u32(sm_b_hi)), bl_lo0 = desc_lo(smem_u32(sm_b_lo));
     int s = 0;
     uint32_t sph = 0;
@@ -286,16 +307,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         mbar_wait(bar_full + 8 * s, sph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t ah = a_lo0 + (uint32_t)(s * 2 * kStageBytes >> 4), al = ah + (kStageBytes >> 4);
+          const uint32_t ah = tmem_a + (uint32_t)(s * kACols), al = ah + kChunkK;   // TMEM columns of this stage
           const uint32_t boff = (uint32_t)(c * (kChunkK / 4) * 128) >> 4;
 #pragma unroll
           for (int j = 0; j < kChunkK / 8; ++j) {
-            const uint64_t dah = desc_make(ah + j * 16, a_sbo), dal = desc_make(al + j * 16, a_sbo);
             const uint64_t dbh = desc_make(bh_lo0 + boff + j * 16, b_sbo);
             const uint64_t dbl = desc_make(bl_lo0 + boff + j * 16, b_sbo);
-            umma_tf32(d_tmem, dah, dbh, idesc, (c | j) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, dal, dbh, idesc, 1u);
-            umma_tf32(d_tmem, dah, dbl, idesc, 1u);
+            umma_tf32_ts(d_tmem, ah + j * 8, dbh, idesc, (c | j) != 0 ? 1u : 0u);
+            umma_tf32_ts(d_tmem, al + j * 8, dbh, idesc, 1u);
+            umma_tf32_ts(d_tmem, ah + j * 8, dbl, idesc, 1u);
           }
           umma_commit(bar_empty + 8 * s);       // stage reusable once these MMAs have read it
           if (c == kch - 1) umma_commit(bar_tfull + 8 * buf);   // accumulator complete
@@ -310,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
-    const uint32_t ncols = 2 * BN;
+    const uint32_t ncols = 512;
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
@@ -361,7 +381,7 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   const int64_t n_tiles = ceil_div(a.m, tc::kTileM);
   int64_t grid = n_tiles * n_slices;
   if (grid > kNumSMs) grid = (kNumSMs / n_slices) * n_slices;
-  const size_t smem = (size_t)2 * k * bn * 4 + (size_t)tc::kStages * 2 * tc::kStageBytes +
+  const size_t smem = (size_t)2 * k * bn * 4 + (size_t)tc::kTransTiles * tc::kTransBytes +
                       (size_t)tc::kEpiWarps * 32 * tc::kStgLd * 4 + 128 * 4 + (2 * tc::kStages + 4) * 8 + 16;
   MPGNN_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc::gemm_rows_tc_kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p);
