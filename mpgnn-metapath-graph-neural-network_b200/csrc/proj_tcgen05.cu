@@ -13,15 +13,17 @@
 //    row tile run next to it, so the second read of the A tile is an L2 hit.
 //  * the A operand is fed to the MMA from TENSOR MEMORY, not shared memory: with three MMAs per
 //    K-step the shared-memory operand fetch (A 4 KB + B 2-4 KB per MMA at ~110 B/clk) was the
-//    bound, so only the small resident B is read from shared memory now.  16 producer warps
-//    stream A with coalesced 128-bit global loads, transpose it through a padded shared tile so
-//    that every thread owns 8 consecutive K values of ONE row, split hi/lo in registers and
-//    tcgen05.st them into a 2-stage ring of TMEM columns (lane = row, column = k).
+//    bound, so only the small resident B is read from shared memory now.  One thread streams raw
+//    fp32 A chunks (128 rows x 32 K) with TMA (cp.async.bulk.tensor, SWIZZLE_128B, OOB rows zero
+//    filled) into a 4-deep shared ring; 16 converter warps read their row slice conflict-free (the
+//    swizzle spreads the 8 rows of a quarter-warp over the 8 bank groups), split hi/lo in registers
+//    and tcgen05.st them into a 4-stage ring of TMEM columns (lane = row, column = k).
 //  * one warp issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step, A from TMEM) from
 //    an elected lane into one of two TMEM accumulators and tcgen05.commit's the barriers.
 //  * 8 epilogue warps (two per TMEM lane quarter, each owning alternate 32-column chunks)
 //    tcgen05.ld the accumulator, apply bias / degree normalisation / relu / dropout in
 //    registers, transpose through a padded shared staging tile and write 64-byte row segments.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -33,17 +35,15 @@ namespace tc {
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                       // fp32 elements per pipeline stage (4 MMA K-steps)
 constexpr int kStages = 4;                        // TMEM A stages in flight (64 columns each)
-constexpr int kTransTiles = 2;                    // shared transpose tiles (only live between STS and LDS)
-constexpr int kPrefetch = 2;                      // chunks in flight in producer registers
+constexpr int kRawStages = 4;                     // TMA-filled raw fp32 chunks in flight
 constexpr int kProducerWarps = 16;
 constexpr int kEpiWarps = 8;
 // Warp roles by warp id: producers first, epilogue warps next (id % 4 = TMEM lane quarter;
 // kProducerWarps is a multiple of 4), the single MMA-issuing warp last.
 constexpr int kMmaWarp = kProducerWarps + kEpiWarps;              // 24
-constexpr int kThreads = (kMmaWarp + 1) * 32;                     // 800
-constexpr int kProducerThreads = kProducerWarps * 32;             // 512
-constexpr int kTransLd = kChunkK + 4;                              // padded transpose-tile row (floats)
-constexpr int kTransBytes = kTileM * kTransLd * 4;                // 18 KB per transpose tile
+constexpr int kTmaWarp = kMmaWarp + 1;                            // 25: one lane issues the TMA loads
+constexpr int kThreads = (kTmaWarp + 1) * 32;                     // 832
+constexpr int kRawBytes = kTileM * kChunkK * 4;                   // 16 KB per raw chunk (128 rows x 128 B)
 constexpr int kACols = 2 * kChunkK;                               // TMEM columns per A stage: hi | lo
 constexpr int kEpiCols = 32;                                      // columns per tcgen05.ld
 constexpr int kStgCols = 16;                                      // columns per staging pass
@@ -79,23 +79,25 @@ __global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, 
   base[(int64_t)k * bn + off] = v - hi;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_a1,
+                                                                   const __grid_constant__ CUtensorMap tmap_a2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int K = p.k1 + p.k2;
   const int BN = p.bn;
   const int b_bytes = K * BN * 4;                         // one of hi / lo
   uint8_t* sm_b_hi = smem;
   uint8_t* sm_b_lo = smem + b_bytes;
-  uint8_t* sm_t = smem + 2 * b_bytes;                     // kStages transpose tiles [128][kTransLd] fp32
-  float* sm_stg = reinterpret_cast<float*>(sm_t + kTransTiles * kTransBytes);       // kEpiWarps x 32 x kStgLd
+  uint8_t* sm_raw = smem + 2 * b_bytes;                   // kRawStages raw chunks, 1024-byte aligned (swizzle)
+  float* sm_stg = reinterpret_cast<float*>(sm_raw + kRawStages * kRawBytes);    // kEpiWarps x 32 x kStgLd
   float* sm_bias = sm_stg + kEpiWarps * 32 * kStgLd;                            // BN floats (slice bias)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_bias + 128);
-  // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], raw_full[kRawStages], raw_empty[kRawStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kRawStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kStages), bar_tempty = smem_u32(bars + 2 * kStages + 2);
+  const uint32_t bar_rfull = smem_u32(bars + 2 * kStages + 4), bar_rempty = smem_u32(bars + 2 * kStages + 4 + kRawStages);
 
   // static work split: this CTA owns slice `slice` and row tiles group, group+n_groups, ...
   const int slice = blockIdx.x % p.n_slices;
@@ -113,6 +115,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, kEpiWarps);
+    }
+    for (int r = 0; r < kRawStages; ++r) {
+      mbar_init(bar_rfull + 8 * r, 1);                 // one arrive.expect_tx + the TMA's byte count
+      mbar_init(bar_rempty + 8 * r, kProducerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -138,83 +144,45 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   const uint32_t tmem_a = tmem_base + (uint32_t)(2 * BN);   // A stages live after the two accumulators
 
   if (warp < kProducerWarps) {
-    // ================================ A producers =======================================
-    // load side: two 16-byte units per thread and chunk, lane -> (row-in-8-group r, 16-byte column c4):
-    // 64-byte global segments, conflict-free stores into the transpose tile (row pitch 144 B).
-    // TMEM side: warp w owns lane quarter w&3 (rows 32*(w&3)+lane) and the 8 K-columns (w>>2)*8...
-    int u_row[2], u_koff[2], u_toff[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int idx = tid + kProducerThreads * u;   // 0..1023
-      const int r = idx & 7, c4 = (idx >> 3) & 3, q = idx >> 5;
-      u_row[u] = (q & 15) * 8 + r;
-      const int core = (q >> 4) * 4 + c4;
-      u_koff[u] = core * 4;
-      u_toff[u] = u_row[u] * (kTransLd * 4) + core * 16;
-    }
+    // ================================ A converters (raw smem -> hi/lo -> TMEM) ===========
+    // converter warps: warp w owns TMEM lane quarter w&3 (rows 32*(w&3)+lane) and the 8 K-columns
+    // (w>>2)*8.. of every chunk = two 16-byte pieces of its row in the raw tile.  The tile is laid out by
+    // the TMA with the 128-byte swizzle: piece c of row r sits at r*128 + ((c ^ (r&7)) * 16).
     const int quarter = warp & 3, colgrp = warp >> 2;
-    const int my_toff = (quarter * 32 + lane) * (kTransLd * 4) + colgrp * 32;
+    const int row = quarter * 32 + lane;
+    const int off0 = row * 128 + (((2 * colgrp) ^ (row & 7)) << 4);
+    const int off1 = row * 128 + (((2 * colgrp + 1) ^ (row & 7)) << 4);
     const uint32_t my_taddr = tmem_a + (uint32_t)(colgrp * 8) + ((uint32_t)(quarter * 32) << 16);
     const int total = my_tiles * kch;
-    float4 buf[kPrefetch][2];
-    // prefetch cursor (tile, chunk) advanced incrementally: no 64-bit div/mod in the loop
-    int pf_tile = 0, pf_c = 0;
-    auto issue = [&](float4 (&dst)[2]) {
-      const int64_t row0 = (int64_t)(group + (int64_t)pf_tile * n_groups) * kTileM;
-      const int kbase = pf_c * kChunkK;
-      const bool first = kbase < p.k1;
-      const float* src = first ? p.a1 : p.a2;
-      const int64_t ld = first ? p.lda1 : p.lda2;
-      const int koff = first ? kbase : kbase - p.k1;
+    int s = 0, rs = 0;
+    uint32_t sph = 0, rph = 0;      // parities of the current use of TMEM stage s / raw stage rs
+    for (int it = 0; it < total; ++it) {
+      const uint8_t* tile = sm_raw + (size_t)rs * kRawBytes;
+      mbar_wait(bar_rfull + 8 * rs, rph);                       // the TMA bytes of this chunk have landed
+      const float4 v0 = *reinterpret_cast<const float4*>(tile + off0);
+      const float4 v1 = *reinterpret_cast<const float4*>(tile + off1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);          // raw stage may be refilled
+      const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int64_t row = row0 + u_row[u];
-        dst[u] = (row < p.m) ? __ldg(reinterpret_cast<const float4*>(src + row * ld + koff + u_koff[u]))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = 0; e < 8; ++e) {
+        const float h = tf32_hi(vv[e]);
+        hi[e] = __float_as_uint(h);
+        lo[e] = __float_as_uint(vv[e] - h);
       }
-      if (++pf_c == kch) { pf_c = 0; ++pf_tile; }
-    };
-#pragma unroll
-    for (int j = 0; j < kPrefetch; ++j)
-      if (j < total) issue(buf[j]);
-    int s = 0;
-    uint32_t sph = 0;      // parity of the current use of stage s
-    for (int it0 = 0; it0 < total; it0 += kPrefetch) {
-#pragma unroll
-      for (int j = 0; j < kPrefetch; ++j) {
-        const int it = it0 + j;
-        if (it < total) {
-          uint8_t* tile = sm_t + (size_t)(it & (kTransTiles - 1)) * kTransBytes;
-          // (1) raw fp32 chunk -> transpose tile.  This tile was last read two chunks ago; the
-          //     named barrier of the previous chunk ordered those reads before these writes.
-          *reinterpret_cast<float4*>(tile + u_toff[0]) = buf[j][0];
-          *reinterpret_cast<float4*>(tile + u_toff[1]) = buf[j][1];
-          asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
-          if (it + kPrefetch < total) issue(buf[j]);
-          // (2) my row slice: 8 consecutive K values of one row -> hi/lo split in registers
-          const float4 v0 = *reinterpret_cast<const float4*>(tile + my_toff);
-          const float4 v1 = *reinterpret_cast<const float4*>(tile + my_toff + 16);
-          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float h = tf32_hi(vv[e]);
-            hi[e] = __float_as_uint(h);
-            lo[e] = __float_as_uint(vv[e] - h);
-          }
-          // (3) TMEM stage s (hi columns [0,32), lo columns [32,64)) once the MMAs that read it are done
-          mbar_wait(bar_empty + 8 * s, sph ^ 1u);
-          tc_fence_after();
-          const uint32_t ta = my_taddr + (uint32_t)(s * kACols);
-          tmem_st8(ta, hi);
-          tmem_st8(ta + kChunkK, lo);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * s);
-          if (++s == kStages) { s = 0; sph ^= 1u; }
-        }
-      }
+      // TMEM stage s (hi columns [0,32), lo columns [32,64)) once the MMAs that read it are done
+      mbar_wait(bar_empty + 8 * s, sph ^ 1u);
+      tc_fence_after();
+      const uint32_t ta = my_taddr + (uint32_t)(s * kACols);
+      tmem_st8(ta, hi);
+      tmem_st8(ta + kChunkK, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (++s == kStages) { s = 0; sph ^= 1u; }
+      if (++rs == kRawStages) { rs = 0; rph ^= 1u; }
     }
   } else if (warp < kMmaWarp) {
     // ================================ epilogue =========================================
@@ -290,6 +258,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
+  } else if (warp == kTmaWarp) {
+    // ================================ TMA producer (one lane) ============================
+    if (lane == 0) {
+      const int total = my_tiles * kch;
+      int rs = 0;
+      uint32_t rph = 0;
+      int tile_i = 0, c = 0;
+      for (int it = 0; it < total; ++it) {
+        mbar_wait(bar_rempty + 8 * rs, rph ^ 1u);             // converters are done with this raw stage
+        const int kbase = c * kChunkK;
+        const bool first = kbase < p.k1;
+        const CUtensorMap* map = first ? &tmap_a1 : &tmap_a2;
+        const int kcoord = first ? kbase : kbase - p.k1;
+        const int64_t row0 = (int64_t)(group + (int64_t)tile_i * n_groups) * kTileM;
+        const uint32_t dst = smem_u32(sm_raw + (size_t)rs * kRawBytes);
+        const uint32_t bar = bar_rfull + 8 * rs;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kRawBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(kcoord), "r"((int)row0)
+            : "memory");
+        if (++c == kch) { c = 0; ++tile_i; }
+        if (++rs == kRawStages) { rs = 0; rph ^= 1u; }
+      }
+    }
   } else {
     // ================================ MMA issuer (whole warp converged; one elected lane issues) ====
     const uint32_t idesc = make_idesc(kTileM, BN);
@@ -337,6 +330,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
 
 }  // namespace tc
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_a_tensor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  static EncodeTiledFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MPGNN_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    MPGNN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, MPGNN_ECUDA,
+                  "proj_tcgen05: cuTensorMapEncodeTiled is not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  // fp32 [rows, cols] row-major with row pitch ld; box = 32 columns (128 bytes, the swizzle span) x 128 rows
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)tc::kChunkK, (cuuint32_t)tc::kTileM};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MPGNN_REQUIRE(r == CUDA_SUCCESS, MPGNN_ECUDA, "proj_tcgen05: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MPGNN_OK;
+}
+
 static int pick_bn(int64_t k, int64_t n) {
   if (n % 128 == 0 && k * 128 * 8 <= tc::kMaxBBytes) return 128;
   if (n % 64 == 0 && k * 64 * 8 <= tc::kMaxBBytes) return 64;
@@ -346,7 +366,7 @@ static int pick_bn(int64_t k, int64_t n) {
 int proj_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags) {
   if (!(flags & MPGNN_F_TF32X3)) return 0;   // the bf16 mode is not built yet
   const int64_t k = k1 + k2;
-  if (m < 1 || m >= (1LL << 37) || k < tc::kChunkK || k > 256) return 0;
+  if (m < 1 || m >= (1LL << 31) - tc::kTileM || k < tc::kChunkK || k > 256) return 0;
   if (k1 % tc::kChunkK != 0 || k2 % tc::kChunkK != 0) return 0;
   if (n % 64 != 0 || n > 65536) return 0;
   return pick_bn(k, n) != 0;
@@ -381,10 +401,15 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   const int64_t n_tiles = ceil_div(a.m, tc::kTileM);
   int64_t grid = n_tiles * n_slices;
   if (grid > kNumSMs) grid = (kNumSMs / n_slices) * n_slices;
-  const size_t smem = (size_t)2 * k * bn * 4 + (size_t)tc::kTransTiles * tc::kTransBytes +
-                      (size_t)tc::kEpiWarps * 32 * tc::kStgLd * 4 + 128 * 4 + (2 * tc::kStages + 4) * 8 + 16;
+  const size_t smem = (size_t)2 * k * bn * 4 + (size_t)tc::kRawStages * tc::kRawBytes +
+                      (size_t)tc::kEpiWarps * 32 * tc::kStgLd * 4 + 128 * 4 +
+                      (2 * tc::kStages + 4 + 2 * tc::kRawStages) * 8 + 16;
+  CUtensorMap map1, map2;
+  MPGNN_PROPAGATE(make_a_tensor_map(&map1, a.a1, a.m, a.k1, a.lda1));
+  if (a.k2 > 0) MPGNN_PROPAGATE(make_a_tensor_map(&map2, a.a2, a.m, a.k2, a.lda2));
+  else map2 = map1;
   MPGNN_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::gemm_rows_tc_kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p);
+  tc::gemm_rows_tc_kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p, map1, map2);
   MPGNN_LAUNCH_CHECK();
   return MPGNN_OK;
 }
