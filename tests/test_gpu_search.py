@@ -86,7 +86,8 @@ def test_greedy_search_step0_end_to_end(fx3):
                                                                              epochs=60))[1]
     union_fn = lambda metas: (torch.manual_seed(30), m.mpgnn_parallel_multiple_x(data_mpgnn, 2, 64, 4, 64, 2, metas,  # noqa: E731
                                                                                  True, epochs=60))[1]
-    res = search.greedy_search(data, data_mpgnn, 2, 64, 4, 64, 2, "synthetic", eval_fn=eval_fn, union_fn=union_fn)
+    res = search.greedy_search(data, data_mpgnn, 2, 64, 4, 64, 2, "synthetic", eval_fn=eval_fn, union_fn=union_fn,
+                               max_depth=0)       # step 0 only; the bag iterations are covered in test_gpu_search_bags.py
     assert res["relations"] == g["actual_relations"].tolist()
     assert np.allclose(res["losses"], g["step0_losses"], rtol=1e-4, atol=1e-7)
     assert res["kept"] == g["step0_best"].tolist()              # bit-exact selection
