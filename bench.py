@@ -144,6 +144,7 @@ def run_ours(args):
     w, root, bias = conv.weight.detach(), conv.root.detach(), conv.bias.detach()
     h = torch.empty(n, f, device=dev)
     y = torch.empty(n, f, device=dev)
+    actmask = torch.empty(n, f // 32, dtype=torch.int32, device=dev)   # [y > 0] bitmask, all the backward needs of y
     gx = torch.empty(n, f, device=dev)
     gw, groot, gb = torch.empty_like(w), torch.empty_like(root), torch.empty_like(bias)
     ws = torch.empty(lib.mpgnn_hop_workspace_bytes(n, f, f), dtype=torch.uint8, device=dev)
@@ -159,8 +160,10 @@ def run_ours(args):
         rel = (step * world + rank) % r
         _lib.check(lib.mpgnn_hop_fwd(graph.handle, rel, _lib.ptr(x_dev), f, _lib.ptr(w), _lib.ptr(root),
                                      _lib.ptr(bias), f, flags_f, DROPOUT_P, 1234, step, None, _lib.ptr(h),
-                                     _lib.ptr(y), _lib.ptr(ws), ws.numel(), stream))
-        _lib.check(lib.mpgnn_hop_bwd(graph.handle, rel, _lib.ptr(x_dev), _lib.ptr(h), _lib.ptr(y), _lib.ptr(gy), f,
+                                     _lib.ptr(y), _lib.ptr(actmask), _lib.ptr(ws), ws.numel(), stream))
+        # the backward takes [y > 0] from the bitmask the forward wrote, as CustomRGCNConv.hop does
+        _lib.check(lib.mpgnn_hop_bwd(graph.handle, rel, _lib.ptr(x_dev), _lib.ptr(h), None, _lib.ptr(actmask),
+                                     _lib.ptr(gy), f,
                                      _lib.ptr(w), _lib.ptr(root), f, flags_b, DROPOUT_P, _lib.ptr(gx), _lib.ptr(gw),
                                      _lib.ptr(groot), _lib.ptr(gb), _lib.ptr(ws), ws.numel(), stream))
         return graph.relation_edges(rel)

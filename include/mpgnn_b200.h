@@ -89,11 +89,14 @@ int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, 
  * (model.py:210-214):   y = drop(relu( mean_r(x) @ W + x @ root + bias )).
  * d_h (N x f_in) receives the aggregated features kept for the backward.
  * d_bias may be NULL.  dropout: p in [0,1); MPGNN_F_DROPOUT_MASK reads d_mask_bits
- * ([N, ceil(f_out/8)] bytes, MSB first); MPGNN_F_DROPOUT_SEED draws from (seed, offset). */
+ * ([N, ceil(f_out/8)] bytes, MSB first); MPGNN_F_DROPOUT_SEED draws from (seed, offset).
+ * d_actmask (may be NULL; needs f_out % 32 == 0) receives the activation bitmask of y,
+ * [N, f_out/32] 32-bit words with bit j of word c = [y(row, 32c+j) > 0]: all the backward
+ * needs of y, 1/32 of its size, and written by the projection epilogue for free. */
 int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t f_in, const float* d_w,
                   const float* d_root, const float* d_bias, int64_t f_out, uint32_t flags, double dropout_p,
                   uint64_t seed, uint64_t offset, const uint8_t* d_mask_bits, float* d_h, float* d_y,
-                  void* d_workspace, int64_t workspace_bytes, void* stream);
+                  uint32_t* d_actmask, void* d_workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- K4: one metapath hop, backward ----------------------------------------------------
  * What autograd derives for the call above:
@@ -102,11 +105,14 @@ int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int6
  *   g_x[j] = (g_z root^T)[j] + sum_{e in E_r, col(e)=j} t[row(e)]   (only with NEED_GX).
  * Reductions over the N rows use a fixed split and a fixed summation order
  * (deterministic, run-to-run and across GPU counts).  Gradients are WRITTEN, not
- * accumulated.  d_gx may be NULL without MPGNN_F_NEED_GX. */
+ * accumulated.  d_gx may be NULL without MPGNN_F_NEED_GX.  [y>0] is taken from d_actmask
+ * (the bitmask mpgnn_hop_fwd wrote) when it is non-NULL, else from d_y; one of the two is
+ * required with MPGNN_F_RELU.  With the bitmask the tensor-core kernels gate g_y while
+ * loading it and g_z is never written to memory. */
 int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, const float* d_h, const float* d_y,
-                  const float* d_gy, int64_t f_in, const float* d_w, const float* d_root, int64_t f_out,
-                  uint32_t flags, double dropout_p, float* d_gx, float* d_gw, float* d_groot, float* d_gbias,
-                  void* d_workspace, int64_t workspace_bytes, void* stream);
+                  const uint32_t* d_actmask, const float* d_gy, int64_t f_in, const float* d_w, const float* d_root,
+                  int64_t f_out, uint32_t flags, double dropout_p, float* d_gx, float* d_gw, float* d_groot,
+                  float* d_gbias, void* d_workspace, int64_t workspace_bytes, void* stream);
 /* Scratch both hop calls need for (N, f_in, f_out). */
 int64_t mpgnn_hop_workspace_bytes(int64_t num_nodes, int64_t f_in, int64_t f_out);
 

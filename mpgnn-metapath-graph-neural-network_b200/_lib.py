@@ -31,9 +31,9 @@ PROTOTYPES = {
     "mpgnn_graph_relation_counts": (_i32, [_ptr, _ptr]),
     "mpgnn_spmm": (_i32, [_ptr, _i64, _i32, _i32, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr]),
     "mpgnn_hop_fwd": (_i32, [_ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _u32, _dbl, _u64, _u64, _ptr, _ptr,
-                             _ptr, _ptr, _i64, _ptr]),
-    "mpgnn_hop_bwd": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _u32, _dbl, _ptr, _ptr,
                              _ptr, _ptr, _ptr, _i64, _ptr]),
+    "mpgnn_hop_bwd": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _u32, _dbl, _ptr,
+                             _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "mpgnn_hop_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "mpgnn_gemm_rows": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _ptr, _i32, _ptr, _i64, _ptr, _i64,
                                _ptr, _i64, _ptr]),

@@ -74,11 +74,12 @@ void graph_free(mpgnn_graph_impl* g);
 int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out);
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
-            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s,
-            const uint64_t* offset_ptr);
-int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y, const float* gy,
-            int64_t f_in, const float* w, const float* root, int64_t f_out, uint32_t flags, double p, float* gx,
-            float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes, cudaStream_t s);
+            const uint8_t* mask_bits, float* h, float* y, uint32_t* actmask, void* ws_ptr, int64_t ws_bytes,
+            cudaStream_t s, const uint64_t* offset_ptr);
+int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y,
+            const uint32_t* actmask, const float* gy, int64_t f_in, const float* w, const float* root, int64_t f_out,
+            uint32_t flags, double p, float* gx, float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes,
+            cudaStream_t s);
 int launch_logsoftmax_nll(const float* logits, int64_t n, int64_t c, const int64_t* idx, const int64_t* y,
                           int64_t n_idx, float* logp, float* loss, float* glogits, void* ws, int64_t ws_bytes,
                           cudaStream_t s);
@@ -241,16 +242,16 @@ int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, 
 int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t f_in, const float* d_w,
                   const float* d_root, const float* d_bias, int64_t f_out, uint32_t flags, double dropout_p,
                   uint64_t seed, uint64_t offset, const uint8_t* d_mask_bits, float* d_h, float* d_y,
-                  void* d_workspace, int64_t workspace_bytes, void* stream) {
+                  uint32_t* d_actmask, void* d_workspace, int64_t workspace_bytes, void* stream) {
   return hop_fwd(impl(g), relation, d_x, f_in, d_w, d_root, d_bias, f_out, flags, dropout_p, seed, offset,
-                 d_mask_bits, d_h, d_y, d_workspace, workspace_bytes, stream_of(stream), nullptr);
+                 d_mask_bits, d_h, d_y, d_actmask, d_workspace, workspace_bytes, stream_of(stream), nullptr);
 }
 
 int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, const float* d_h, const float* d_y,
-                  const float* d_gy, int64_t f_in, const float* d_w, const float* d_root, int64_t f_out,
-                  uint32_t flags, double dropout_p, float* d_gx, float* d_gw, float* d_groot, float* d_gbias,
-                  void* d_workspace, int64_t workspace_bytes, void* stream) {
-  return hop_bwd(impl(g), relation, d_x, d_h, d_y, d_gy, f_in, d_w, d_root, f_out, flags, dropout_p, d_gx, d_gw,
+                  const uint32_t* d_actmask, const float* d_gy, int64_t f_in, const float* d_w, const float* d_root,
+                  int64_t f_out, uint32_t flags, double dropout_p, float* d_gx, float* d_gw, float* d_groot,
+                  float* d_gbias, void* d_workspace, int64_t workspace_bytes, void* stream) {
+  return hop_bwd(impl(g), relation, d_x, d_h, d_y, d_actmask, d_gy, f_in, d_w, d_root, f_out, flags, dropout_p, d_gx, d_gw,
                  d_groot, d_gbias, d_workspace, workspace_bytes, stream_of(stream));
 }
 

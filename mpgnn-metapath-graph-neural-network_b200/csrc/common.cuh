@@ -105,6 +105,9 @@ struct GemmRowsArgs {
   uint64_t seed; uint64_t offset; const uint8_t* mask_bits;
   const uint64_t* offset_ptr;             // optional device word added to `offset` (CUDA-graph replays)
   float* out; int64_t ldo;
+  // activation bitmask (tcgen05 path only): word (row, c) bit j = [out(row, 32c+j) > 0]
+  uint32_t* actmask_out;                  // written by the epilogue when non-null (needs n % 32 == 0)
+  const uint32_t* a1_actmask; float a1_scale;   // A1(r,k) := bit(r,k) ? A1(r,k)*a1_scale : 0 (k2 must be 0)
 };
 int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s);
 
@@ -119,6 +122,7 @@ struct GemmTnArgs {
   float* out2; int64_t ldo2;   // rows [k1,k1+k2)
   float* out_ones;             // [N] (row k1+k2) or null
   float* partials; int64_t partial_capacity_floats;
+  const uint32_t* b_actmask; float b_scale;     // tcgen05 path: B(r,c) := bit(r,c) ? B(r,c)*b_scale : 0
 };
 int launch_gemm_tn(const GemmTnArgs& a, cudaStream_t s);
 int64_t gemm_tn_partial_floats(int64_t m, int64_t ktot, int64_t n);
@@ -126,25 +130,52 @@ int64_t gemm_tn_partial_floats(int64_t m, int64_t ktot, int64_t n);
 int launch_pack_b(float* dst, int64_t ldd, const float* src, int64_t src_ld_k, int64_t src_ld_n, int64_t k,
                   int64_t n, cudaStream_t s);
 int launch_relu_dropout_bwd(const float* gy, const float* y, float scale, float* gz, int64_t count, cudaStream_t s);
+int launch_pack_actmask(const float* y, int64_t m, int64_t n, uint32_t* mask, cudaStream_t s);
+int launch_relu_dropout_bwd_mask(const float* gy, const uint32_t* mask, float scale, float* gz, int64_t m, int64_t n,
+                                 cudaStream_t s);
 
 int launch_spmm(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
                 int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s);
 
 // ---- device helpers ---------------------------------------------------------------------
-// Counter-based dropout randomness: one 64-bit SplitMix64-mixed word per block of 4 consecutive
-// output elements (elem >> 2), keyed by (seed, offset).  Stateless, so the stream does not depend
-// on the launch geometry and both projection paths (SIMT / tcgen05) draw identical masks.  Element
-// j of the block keeps its value iff its 16-bit lane >= thr16 = round(p * 65536).
-__device__ __forceinline__ uint64_t dropout_word(uint64_t seed, uint64_t offset, uint64_t blk) {
-  uint64_t z = blk * 0x9E3779B97F4A7C15ull + (seed ^ (offset * 0xD1B54A32D192ED03ull));
+// Counter-based dropout randomness, stateless (the stream does not depend on the launch geometry,
+// so the SIMT and tcgen05 projections draw identical masks) and cheap where it is hot:
+//   launch key = splitmix64(seed ^ splitmix64(offset))              once per launch / thread
+//   row key    = splitmix64(launch key + row * GOLDEN)              once per output row
+//   block word = 4 Philox-style rounds (32x32->64 multiply, xor) of (lo32(row key) + blk*GOLDEN32,
+//                hi32(row key))                                      once per 4 consecutive columns
+// i.e. 9 integer instructions per 4 elements in the epilogue.  Element j of block blk = col/4 keeps
+// its value iff 16-bit lane j of the 64-bit block word (.x = lanes 0,1; .y = lanes 2,3) is
+// >= thr16 = round(p * 65536).
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
-
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t elem, uint32_t thr16) {
-  const uint64_t w = dropout_word(seed, offset, elem >> 2);
-  return (uint32_t)((w >> (16 * (elem & 3))) & 0xFFFFu) >= thr16;
+__host__ __device__ __forceinline__ uint64_t dropout_launch_key(uint64_t seed, uint64_t offset) {
+  return splitmix64(seed ^ splitmix64(offset));
+}
+__host__ __device__ __forceinline__ uint64_t dropout_row_key(uint64_t launch_key, uint64_t row) {
+  return splitmix64(launch_key + row * 0x9E3779B97F4A7C15ull);
+}
+__host__ __device__ __forceinline__ uint2 dropout_block(uint64_t row_key, uint32_t blk) {
+  uint32_t c0 = (uint32_t)row_key + blk * 0x9E3779B9u, c1 = (uint32_t)(row_key >> 32);
+  const uint32_t rk[4] = {0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint64_t prod = (uint64_t)c0 * 0xD2511F53ull;
+    c0 = (uint32_t)(prod >> 32) ^ c1 ^ rk[r];
+    c1 = (uint32_t)prod;
+  }
+  uint2 w;
+  w.x = c1; w.y = c0;
+  return w;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t row, uint64_t col, uint32_t thr16) {
+  const uint2 w = dropout_block(dropout_row_key(dropout_launch_key(seed, offset), row), (uint32_t)(col >> 2));
+  const uint32_t half = (col & 2) ? w.y : w.x;
+  return ((half >> (16 * (col & 1))) & 0xFFFFu) >= thr16;
 }
 
 static inline uint32_t dropout_threshold16(double p) {

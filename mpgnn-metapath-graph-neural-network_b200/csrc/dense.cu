@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.gate != nullptr) v = (__ldg(a.gate + row * a.ldgate + col) > 0.f) ? v : 0.f;
       if (a.dropout_mode == 1) {
-        v = dropout_keep(a.seed, drop_off, (uint64_t)row * (uint64_t)a.n + (uint64_t)col, a.dropout_thr16) ? v * scale : 0.f;
+        v = dropout_keep(a.seed, drop_off, (uint64_t)row, (uint64_t)col, a.dropout_thr16) ? v * scale : 0.f;
       } else if (a.dropout_mode == 2) {
         const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
         v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;
@@ -281,6 +281,57 @@ int launch_relu_dropout_bwd(const float* gy, const float* y, float scale, float*
                                                                reinterpret_cast<float4*>(gz), work);
   else
     relu_dropout_bwd_kernel<<<(unsigned)blocks, 256, 0, s>>>(gy, y, scale, gz, count);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+// activation bitmask of a contiguous [m, n] matrix (n % 32 == 0): word i bit j = [y[32 i + j] > 0]
+__global__ void pack_actmask_kernel(const float* __restrict__ y, int64_t count, uint32_t* __restrict__ mask) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {   // count % 32 == 0
+    const uint32_t w = __ballot_sync(0xFFFFFFFFu, y[i] > 0.f);
+    if ((threadIdx.x & 31) == 0) mask[i >> 5] = w;
+  }
+}
+
+int launch_pack_actmask(const float* y, int64_t m, int64_t n, uint32_t* mask, cudaStream_t s) {
+  MPGNN_REQUIRE(n % 32 == 0, MPGNN_ENOTSUP, "actmask: the feature width must be a multiple of 32 (got %lld)", (long long)n);
+  const int64_t count = m * n;
+  if (count <= 0) return MPGNN_OK;
+  int64_t blocks = ceil_div(count, 256);
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  pack_actmask_kernel<<<(unsigned)blocks, 256, 0, s>>>(y, count, mask);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
+__global__ void relu_dropout_bwd_mask_kernel(const float4* __restrict__ gy, const uint32_t* __restrict__ mask, float scale,
+                                             float4* __restrict__ gz, int64_t count4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count4; i += stride) {
+    const float4 g = gy[i];
+    const uint32_t nib = (__ldg(mask + (i >> 3)) >> ((i & 7) * 4)) & 0xFu;
+    float4 o;
+    o.x = (nib & 1u) ? g.x * scale : 0.f;
+    o.y = (nib & 2u) ? g.y * scale : 0.f;
+    o.z = (nib & 4u) ? g.z * scale : 0.f;
+    o.w = (nib & 8u) ? g.w * scale : 0.f;
+    gz[i] = o;
+  }
+}
+
+int launch_relu_dropout_bwd_mask(const float* gy, const uint32_t* mask, float scale, float* gz, int64_t m, int64_t n,
+                                 cudaStream_t s) {
+  MPGNN_REQUIRE(n % 32 == 0, MPGNN_ENOTSUP, "actmask: the feature width must be a multiple of 32 (got %lld)", (long long)n);
+  MPGNN_REQUIRE(((uintptr_t)gy % 16 == 0) && ((uintptr_t)gz % 16 == 0), MPGNN_EINVAL, "actmask: unaligned gradient");
+  const int64_t work = m * n / 4;
+  if (work <= 0) return MPGNN_OK;
+  int64_t blocks = ceil_div(work, 256);
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  relu_dropout_bwd_mask_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(gy), mask, scale,
+                                                                 reinterpret_cast<float4*>(gz), work);
   MPGNN_LAUNCH_CHECK();
   return MPGNN_OK;
 }

@@ -36,8 +36,8 @@ int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
 
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
-            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s,
-            const uint64_t* offset_ptr) {
+            const uint8_t* mask_bits, float* h, float* y, uint32_t* actmask, void* ws_ptr, int64_t ws_bytes,
+            cudaStream_t s, const uint64_t* offset_ptr) {
   MPGNN_REQUIRE(g && x && w && root && h && y, MPGNN_EINVAL, "hop_fwd: NULL argument");
   MPGNN_REQUIRE(rel >= 0 && rel < g->r, MPGNN_ERANGE, "hop_fwd: relation %lld outside [0,%lld)", (long long)rel,
                 (long long)g->r);
@@ -46,6 +46,8 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   MPGNN_REQUIRE(!(drop_seed && drop_mask), MPGNN_EINVAL, "hop_fwd: both dropout modes set");
   MPGNN_REQUIRE(!(drop_seed || drop_mask) || (p >= 0.0 && p < 1.0), MPGNN_EINVAL, "hop_fwd: dropout p=%g", p);
   MPGNN_REQUIRE(!drop_mask || mask_bits, MPGNN_EINVAL, "hop_fwd: mask mode without mask");
+  MPGNN_REQUIRE(actmask == nullptr || f_out % 32 == 0, MPGNN_ENOTSUP,
+                "hop_fwd: the activation bitmask needs f_out %% 32 == 0 (got %lld)", (long long)f_out);
   Workspace ws(ws_ptr, ws_bytes);
   float* bp = ws.take<float>(fwd_ws_floats(f_in, f_out));
   MPGNN_REQUIRE(bp != nullptr, MPGNN_EINVAL, "hop_fwd: workspace too small");
@@ -71,16 +73,28 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   a.out = y; a.ldo = f_out;
   if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
     ScopedTimer tm("proj_fwd_tcgen05", s);
+    a.actmask_out = actmask;                           // written by the epilogue, no extra pass
     return launch_proj_tcgen05_ws(a, flags, bp + align_up(2 * f_in * f_out, 64), s);
   }
-  ScopedTimer tm("proj_fwd_simt", s);
-  return launch_gemm_rows(a, s);
+  {
+    ScopedTimer tm("proj_fwd_simt", s);
+    MPGNN_PROPAGATE(launch_gemm_rows(a, s));
+  }
+  if (actmask != nullptr) {
+    ScopedTimer tm("pack_actmask", s);
+    MPGNN_PROPAGATE(launch_pack_actmask(y, g->n, f_out, actmask, s));
+  }
+  return MPGNN_OK;
 }
 
-int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y, const float* gy,
-            int64_t f_in, const float* w, const float* root, int64_t f_out, uint32_t flags, double p, float* gx,
-            float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes, cudaStream_t s) {
-  MPGNN_REQUIRE(g && x && h && y && gy && w && root && gw && groot, MPGNN_EINVAL, "hop_bwd: NULL argument");
+int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y,
+            const uint32_t* actmask, const float* gy, int64_t f_in, const float* w, const float* root, int64_t f_out,
+            uint32_t flags, double p, float* gx, float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes,
+            cudaStream_t s) {
+  MPGNN_REQUIRE(g && x && h && gy && w && root && gw && groot, MPGNN_EINVAL, "hop_bwd: NULL argument");
+  MPGNN_REQUIRE(!(flags & MPGNN_F_RELU) || y || actmask, MPGNN_EINVAL, "hop_bwd: RELU needs d_y or d_actmask");
+  MPGNN_REQUIRE(actmask == nullptr || f_out % 32 == 0, MPGNN_ENOTSUP,
+                "hop_bwd: the activation bitmask needs f_out %% 32 == 0 (got %lld)", (long long)f_out);
   MPGNN_REQUIRE(rel >= 0 && rel < g->r, MPGNN_ERANGE, "hop_bwd: relation %lld outside [0,%lld)", (long long)rel,
                 (long long)g->r);
   const bool need_gx = flags & MPGNN_F_NEED_GX;
@@ -97,12 +111,22 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   float* t = need_gx ? ws.take<float>(align_up(n * 2 * f_in, 64)) : nullptr;
   MPGNN_REQUIRE(gz && partials && bp2 && bp2_img && (!need_gx || t), MPGNN_EINVAL, "hop_bwd: workspace too small");
 
+  // g_z = g_y * [y > 0] * 1/(1-p).  With the activation bitmask and both tensor-core kernels available
+  // the gating is fused into their operand loads (g_z is never materialised); otherwise one pass writes it.
+  const bool tc_w = wgrad_tcgen05_supported(n, f_in, f_in, f_out, flags);
+  const bool tc_d = (flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(n, f_out, 0, 2 * f_in, flags);
+  const float scale = drop ? (float)(1.0 / (1.0 - p)) : 1.f;
   const float* gz_src = gy;
+  const uint32_t* fused_mask = nullptr;
   if (flags & MPGNN_F_RELU) {
-    const float scale = drop ? (float)(1.0 / (1.0 - p)) : 1.f;
-    ScopedTimer tm("relu_dropout_bwd", s);
-    MPGNN_PROPAGATE(launch_relu_dropout_bwd(gy, y, scale, gz, n * f_out, s));
-    gz_src = gz;
+    if (actmask != nullptr && tc_w && (!need_gx || tc_d)) {
+      fused_mask = actmask;
+    } else {
+      ScopedTimer tm("relu_dropout_bwd", s);
+      if (actmask != nullptr) MPGNN_PROPAGATE(launch_relu_dropout_bwd_mask(gy, actmask, scale, gz, n, f_out, s));
+      else MPGNN_PROPAGATE(launch_relu_dropout_bwd(gy, y, scale, gz, n * f_out, s));
+      gz_src = gz;
+    }
   }
   GemmTnArgs tn{};
   tn.a1 = h; tn.lda1 = f_in; tn.k1 = f_in;
@@ -113,7 +137,8 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   tn.out2 = groot; tn.ldo2 = f_out;
   tn.out_ones = gbias;
   tn.partials = partials; tn.partial_capacity_floats = part_floats;
-  if (wgrad_tcgen05_supported(n, f_in, f_in, f_out, flags)) {
+  tn.b_actmask = fused_mask; tn.b_scale = scale;
+  if (tc_w) {
     ScopedTimer tm("wgrad_tn_tcgen05", s);
     MPGNN_PROPAGATE(launch_wgrad_tcgen05(tn, partials, s));
   } else {
@@ -131,7 +156,8 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
     a.b = bp2; a.m = n; a.n = 2 * f_in;
     a.deg_ptr = g->csr_ptr + rel * n; a.deg_cols = f_in;
     a.out = t; a.ldo = 2 * f_in;
-    if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
+    a.a1_actmask = fused_mask; a.a1_scale = scale;
+    if (tc_d) {
       ScopedTimer tm("dgrad_nt_tcgen05", s);
       MPGNN_PROPAGATE(launch_proj_tcgen05_ws(a, flags, bp2_img, s));
     } else {

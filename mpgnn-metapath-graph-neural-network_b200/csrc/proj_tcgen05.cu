@@ -21,8 +21,11 @@
 //  * one warp issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step, A from TMEM) from
 //    an elected lane into one of two TMEM accumulators and tcgen05.commit's the barriers.
 //  * 8 epilogue warps (two per TMEM lane quarter, each owning alternate 32-column chunks)
-//    tcgen05.ld the accumulator, apply bias / degree normalisation / relu / dropout in
-//    registers, transpose through a padded shared staging tile and write 64-byte row segments.
+//    tcgen05.ld the accumulator and hand it back to the MMA warp at once, apply bias / degree
+//    normalisation / relu / dropout in registers (the kernel is specialised on the dropout mode
+//    and the degree scaling; the random bits cost 9 integer instructions per 4 elements), put the
+//    32x32 block into a swizzled staging tile and let one lane TMA-store it (rows past M are
+//    clipped by the tensor map).  It also emits the activation bitmask [out > 0] the backward uses.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -46,8 +49,7 @@ constexpr int kThreads = (kTmaWarp + 1) * 32;                     // 832
 constexpr int kRawBytes = kTileM * kChunkK * 4;                   // 16 KB per raw chunk (128 rows x 128 B)
 constexpr int kACols = 2 * kChunkK;                               // TMEM columns per A stage: hi | lo
 constexpr int kEpiCols = 32;                                      // columns per tcgen05.ld
-constexpr int kStgCols = 16;                                      // columns per staging pass
-constexpr int kStgLd = kStgCols + 4;                              // padded staging row (floats)
+constexpr int kStgBytes = 32 * kEpiCols * 4;                      // per-warp TMA-store staging tile (32 rows x 128 B)
 constexpr int kMaxBBytes = 131072;                                // hi + lo of the resident slice
 
 struct Params {
@@ -61,6 +63,8 @@ struct Params {
   int dropout_mode; uint32_t dropout_thr16; float dropout_scale; uint64_t seed; uint64_t offset;
   const uint8_t* mask_bits; const uint64_t* offset_ptr;
   float* out; int64_t ldo;
+  uint32_t* actmask_out;                       // [m][n/32] words, bit j of word c = [out(row, 32c+j) > 0]
+  const uint32_t* a_actmask; float a_scale;    // A(r,k) := bit(r,k) ? A(r,k)*a_scale : 0 ([m][K/32] words, k2 == 0)
 };
 
 // Re-lays B[K,N] (row-major) into per-slice UMMA images: element (n,k) of a slice lives at byte
@@ -79,8 +83,10 @@ __global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, 
   base[(int64_t)k * bn + off] = v - hi;
 }
 
+template <int kDrop, bool kDeg>      // kDrop: 0 none, 1 seeded, 2 mask bits; kDeg: divide the first deg_cols columns by deg
 __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_a1,
-                                                                   const __grid_constant__ CUtensorMap tmap_a2) {
+                                                                   const __grid_constant__ CUtensorMap tmap_a2,
+                                                                   const __grid_constant__ CUtensorMap tmap_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int K = p.k1 + p.k2;
   const int BN = p.bn;
@@ -88,8 +94,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   uint8_t* sm_b_hi = smem;
   uint8_t* sm_b_lo = smem + b_bytes;
   uint8_t* sm_raw = smem + 2 * b_bytes;                   // kRawStages raw chunks, 1024-byte aligned (swizzle)
-  float* sm_stg = reinterpret_cast<float*>(sm_raw + kRawStages * kRawBytes);    // kEpiWarps x 32 x kStgLd
-  float* sm_bias = sm_stg + kEpiWarps * 32 * kStgLd;                            // BN floats (slice bias)
+  uint8_t* sm_stg = sm_raw + kRawStages * kRawBytes;                            // kEpiWarps staging tiles (1024-aligned)
+  float* sm_bias = reinterpret_cast<float*>(sm_stg + kEpiWarps * kStgBytes);    // BN floats (slice bias)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_bias + 128);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], raw_full[kRawStages], raw_empty[kRawStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kRawStages);
@@ -156,14 +162,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     const int total = my_tiles * kch;
     int s = 0, rs = 0;
     uint32_t sph = 0, rph = 0;      // parities of the current use of TMEM stage s / raw stage rs
+    // fused ReLU/dropout backward (dgrad): the operand is g_y gated by the activation bitmask of y;
+    // the 32-bit word of (row, chunk) is fetched one chunk ahead
+    const bool masked = p.a_actmask != nullptr;
+    int mc = 0, mtile = 0;
+    auto load_mask_word = [&]() -> uint32_t {
+      const int64_t grow = (int64_t)(group + (int64_t)mtile * n_groups) * kTileM + row;
+      const uint32_t w = grow < p.m ? __ldg(p.a_actmask + grow * kch + mc) : 0u;
+      if (++mc == kch) { mc = 0; ++mtile; }
+      return w;
+    };
+    uint32_t mw = (masked && total > 0) ? load_mask_word() : 0u;
     for (int it = 0; it < total; ++it) {
       const uint8_t* tile = sm_raw + (size_t)rs * kRawBytes;
+      const uint32_t mw_next = (masked && it + 1 < total) ? load_mask_word() : 0u;
       mbar_wait(bar_rfull + 8 * rs, rph);                       // the TMA bytes of this chunk have landed
       const float4 v0 = *reinterpret_cast<const float4*>(tile + off0);
       const float4 v1 = *reinterpret_cast<const float4*>(tile + off1);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);          // raw stage may be refilled
-      const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      if (masked) {
+        const uint32_t bits = mw >> (colgrp * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) vv[e] = ((bits >> e) & 1u) ? vv[e] * p.a_scale : 0.f;
+        mw = mw_next;
+      }
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -189,75 +213,96 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     const int ew = warp - kProducerWarps;        // 0..7
     const int quarter = ew & 3;                  // == warp % 4: the TMEM lanes this warp may read
     const int half = ew >> 2;                    // owns 32-column chunks cc = half, half+2, ...
-    float* stg = sm_stg + ew * 32 * kStgLd;
+    // staging tile of this warp in the TMA SWIZZLE_128B layout: 16-byte piece c of row r at r*128 + ((c ^ (r&7))*16)
+    const uint32_t stg_tile = smem_u32(sm_stg + ew * kStgBytes);
+    const uint32_t stg_row = stg_tile + (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
     const int64_t mask_ld = (p.n + 7) / 8;
-    const bool do_drop_seed = p.dropout_mode == 1, do_drop_mask = p.dropout_mode == 2;
-    const uint64_t drop_off = p.offset + (p.offset_ptr != nullptr ? *p.offset_ptr : 0ull);
+    const int n_cc = BN / kEpiCols;
+    const float relu_floor = p.relu ? 0.f : -INFINITY;
+    const uint32_t thr_hi = p.dropout_thr16 << 16;
+    uint64_t launch_key = 0;
+    if (kDrop == 1) launch_key = dropout_launch_key(p.seed, p.offset + (p.offset_ptr != nullptr ? *p.offset_ptr : 0ull));
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int buf = ti & 1;
       const uint32_t ph = (uint32_t)((ti >> 1) & 1);
       const int64_t row0 = (int64_t)(group + (int64_t)ti * n_groups) * kTileM;
       const int64_t row = row0 + quarter * 32 + lane;       // the TMEM lane this thread reads
       float inv_deg = 1.f;
-      if (p.deg_ptr != nullptr && row < p.m) {
+      if (kDeg && row < p.m) {
         const int d = __ldg(p.deg_ptr + row + 1) - __ldg(p.deg_ptr + row);
         inv_deg = 1.0f / (float)max(d, 1);
       }
+      uint64_t row_key = 0;
+      if (kDrop == 1) row_key = dropout_row_key(launch_key, (uint64_t)row);
       mbar_wait(bar_tfull + 8 * buf, ph);
       tc_fence_after();
-      for (int cc = half; cc < BN / kEpiCols; cc += 2) {
+      for (int cc = half; cc < n_cc; cc += 2) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + cc * kEpiCols) + ((uint32_t)(quarter * 32) << 16);
         tmem_ld32(taddr, v);
+        if (cc + 2 >= n_cc) {        // this warp's last read of the accumulator: hand it back before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
         const int lcol0 = cc * kEpiCols;                    // column inside the slice
         const int col0 = slice * BN + lcol0;                // global output column
-        const bool scale_deg = col0 < p.deg_cols;           // deg_cols is a multiple of 32 (checked on host)
+        const bool scale_deg = kDeg && col0 < p.deg_cols;   // deg_cols is a multiple of 32 (checked on host)
+        float o[32];
 #pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {                    // two staging passes of 16 columns
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = *reinterpret_cast<const float4*>(sm_bias + lcol0 + 4 * q);
+          const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int e0 = hp * 16 + 4 * q;                 // first of 4 consecutive elements
-            uint64_t rnd = 0;
-            if (do_drop_seed)
-              rnd = dropout_word(p.seed, drop_off, ((uint64_t)row * (uint64_t)p.n + (uint64_t)(col0 + e0)) >> 2);
+          for (int j = 0; j < 4; ++j) {
+            float x = __uint_as_float(v[4 * q + j]) + bb[j];
+            if (scale_deg) x *= inv_deg;
+            o[4 * q + j] = fmaxf(x, relu_floor);
+          }
+          if (kDrop == 1) {
+            const uint2 w = dropout_block(row_key, (uint32_t)(col0 >> 2) + (uint32_t)q);
+            o[4 * q + 0] = (w.x << 16) >= thr_hi ? o[4 * q + 0] * p.dropout_scale : 0.f;
+            o[4 * q + 1] = w.x >= thr_hi ? o[4 * q + 1] * p.dropout_scale : 0.f;
+            o[4 * q + 2] = (w.y << 16) >= thr_hi ? o[4 * q + 2] * p.dropout_scale : 0.f;
+            o[4 * q + 3] = w.y >= thr_hi ? o[4 * q + 3] * p.dropout_scale : 0.f;
+          } else if (kDrop == 2) {
             uint32_t mbits = 0;
-            if (do_drop_mask && row < p.m) {
-              const int c = col0 + e0;                      // multiple of 4: the nibble of one byte
+            if (row < p.m) {
+              const int c = col0 + 4 * q;                   // multiple of 4: the nibble of one byte
               const uint32_t byte = __ldg(p.mask_bits + row * mask_ld + (c >> 3));
               mbits = (c & 4) ? (byte & 0xFu) : (byte >> 4);   // MSB-first: bit 3 = first element
             }
-            float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x = __uint_as_float(v[e0 + j]) + sm_bias[lcol0 + e0 + j];
-              if (scale_deg) x *= inv_deg;
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (do_drop_seed)
-                x = ((uint32_t)(rnd >> (16 * j)) & 0xFFFFu) >= p.dropout_thr16 ? x * p.dropout_scale : 0.f;
-              else if (do_drop_mask)
-                x = ((mbits >> (3 - j)) & 1u) ? x * p.dropout_scale : 0.f;
-              o[j] = x;
-            }
-            *reinterpret_cast<float4*>(stg + lane * kStgLd + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            for (int j = 0; j < 4; ++j) o[4 * q + j] = ((mbits >> (3 - j)) & 1u) ? o[4 * q + j] * p.dropout_scale : 0.f;
           }
-          __syncwarp();
-          // transposed read: 4 lanes cover one 64-byte row segment; a quarter-warp reads rows
-          // {j, j+4} so that its 8 lanes hit 8 distinct bank groups (row stride 20 floats)
+        }
+        if (p.actmask_out != nullptr) {
+          uint32_t act = 0;                                 // [out > 0] of this thread's 32 columns
 #pragma unroll
-          for (int r8 = 0; r8 < 32; r8 += 8) {
-            const int rl = r8 + ((lane >> 3) & 3) + 4 * ((lane >> 2) & 1);
-            const int64_t grow = row0 + quarter * 32 + rl;
-            const float4 val = *reinterpret_cast<const float4*>(stg + rl * kStgLd + 4 * (lane & 3));
-            if (grow < p.m)
-              *reinterpret_cast<float4*>(p.out + grow * p.ldo + col0 + hp * 16 + 4 * (lane & 3)) = val;
-          }
-          __syncwarp();
+          for (int e = 0; e < 32; ++e) act |= (o[e] > 0.f ? 1u : 0u) << e;
+          if (row < p.m) p.actmask_out[row * (int64_t)(p.n >> 5) + (col0 >> 5)] = act;
+        }
+        // the previous TMA store of this warp must have finished READING the staging tile
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row + (((uint32_t)q ^ sw) << 4)), "f"(o[4 * q]),
+                       "f"(o[4 * q + 1]), "f"(o[4 * q + 2]), "f"(o[4 * q + 3])
+                       : "memory");
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmap_out)),
+                       "r"(stg_tile), "r"(col0), "r"((int)(row0 + quarter * 32))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == kTmaWarp) {
     // ================================ TMA producer (one lane) ============================
     if (lane == 0) {
@@ -335,7 +380,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_a_tensor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+static int make_tensor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   static EncodeTiledFn encode = nullptr;
   if (encode == nullptr) {
     void* fn = nullptr;
@@ -345,10 +390,10 @@ static int make_a_tensor_map(CUtensorMap* map, const float* base, int64_t rows, 
                   "proj_tcgen05: cuTensorMapEncodeTiled is not available");
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  // fp32 [rows, cols] row-major with row pitch ld; box = 32 columns (128 bytes, the swizzle span) x 128 rows
+  // fp32 [rows, cols] row-major with row pitch ld; box = 32 columns (128 bytes, the swizzle span) x box_rows rows
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)tc::kChunkK, (cuuint32_t)tc::kTileM};
+  const cuuint32_t box[2] = {(cuuint32_t)tc::kChunkK, (cuuint32_t)box_rows};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -378,6 +423,8 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   const int64_t k = a.k1 + a.k2;
   MPGNN_REQUIRE(proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags), MPGNN_ENOTSUP, "proj_tcgen05: unsupported shape");
   MPGNN_REQUIRE(a.gate == nullptr, MPGNN_ENOTSUP, "proj_tcgen05: gate epilogue not supported");
+  MPGNN_REQUIRE(a.a1_actmask == nullptr || a.k2 == 0, MPGNN_ENOTSUP, "proj_tcgen05: operand mask needs k2 == 0");
+  MPGNN_REQUIRE(a.actmask_out == nullptr || a.n % 32 == 0, MPGNN_ENOTSUP, "proj_tcgen05: actmask needs n % 32 == 0");
   MPGNN_REQUIRE(a.deg_ptr == nullptr || a.deg_cols % tc::kEpiCols == 0, MPGNN_ENOTSUP,
                 "proj_tcgen05: deg_cols must be a multiple of 32");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -398,20 +445,33 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   p.dropout_mode = a.dropout_mode; p.dropout_thr16 = a.dropout_thr16; p.dropout_scale = a.dropout_scale;
   p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits; p.offset_ptr = a.offset_ptr;
   p.out = a.out; p.ldo = a.ldo;
+  p.actmask_out = a.actmask_out; p.a_actmask = a.a1_actmask; p.a_scale = a.a1_scale;
   const int64_t n_tiles = ceil_div(a.m, tc::kTileM);
   int64_t grid = n_tiles * n_slices;
   if (grid > kNumSMs) grid = (kNumSMs / n_slices) * n_slices;
   const size_t smem = (size_t)2 * k * bn * 4 + (size_t)tc::kRawStages * tc::kRawBytes +
-                      (size_t)tc::kEpiWarps * 32 * tc::kStgLd * 4 + 128 * 4 +
+                      (size_t)tc::kEpiWarps * tc::kStgBytes + 128 * 4 +
                       (2 * tc::kStages + 4 + 2 * tc::kRawStages) * 8 + 16;
-  CUtensorMap map1, map2;
-  MPGNN_PROPAGATE(make_a_tensor_map(&map1, a.a1, a.m, a.k1, a.lda1));
-  if (a.k2 > 0) MPGNN_PROPAGATE(make_a_tensor_map(&map2, a.a2, a.m, a.k2, a.lda2));
+  CUtensorMap map1, map2, map_out;
+  MPGNN_PROPAGATE(make_tensor_map(&map1, a.a1, a.m, a.k1, a.lda1, tc::kTileM));
+  if (a.k2 > 0) MPGNN_PROPAGATE(make_tensor_map(&map2, a.a2, a.m, a.k2, a.lda2, tc::kTileM));
   else map2 = map1;
-  MPGNN_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_rows_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::gemm_rows_tc_kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p, map1, map2);
-  MPGNN_LAUNCH_CHECK();
-  return MPGNN_OK;
+  MPGNN_PROPAGATE(make_tensor_map(&map_out, a.out, a.m, a.n, a.ldo, 32));
+  auto launch = [&](auto kernel) -> int {
+    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p, map1, map2, map_out);
+    MPGNN_LAUNCH_CHECK();
+    return MPGNN_OK;
+  };
+  const bool deg = p.deg_ptr != nullptr && p.deg_cols > 0;
+  switch (p.dropout_mode * 2 + (deg ? 1 : 0)) {
+    case 0: return launch(tc::gemm_rows_tc_kernel<0, false>);
+    case 1: return launch(tc::gemm_rows_tc_kernel<0, true>);
+    case 2: return launch(tc::gemm_rows_tc_kernel<1, false>);
+    case 3: return launch(tc::gemm_rows_tc_kernel<1, true>);
+    case 4: return launch(tc::gemm_rows_tc_kernel<2, false>);
+    default: return launch(tc::gemm_rows_tc_kernel<2, true>);
+  }
 }
 
 }  // namespace mpgnn

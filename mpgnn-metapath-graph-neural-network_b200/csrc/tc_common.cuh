@@ -98,11 +98,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// hi = v rounded to nearest TF32 (low 13 mantissa bits zero afterwards): |v - hi| <= 2^-12 |v|
+// hi = v rounded to nearest TF32, ties away from zero (low 13 mantissa bits zero afterwards):
+// |v - hi| <= 2^-12 |v|.  Same values as cvt.rna.tf32.f32 for every finite input, but two integer
+// instructions instead of the four the conversion expands to; NaN/Inf still poison the result
+// through the lo = v - hi term.
 __device__ __forceinline__ float tf32_hi(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 
 

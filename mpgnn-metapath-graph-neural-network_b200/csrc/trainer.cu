@@ -15,11 +15,12 @@ namespace mpgnn {
 int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out);
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
-            const uint8_t* mask_bits, float* h, float* y, void* ws_ptr, int64_t ws_bytes, cudaStream_t s,
-            const uint64_t* offset_ptr);
-int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y, const float* gy,
-            int64_t f_in, const float* w, const float* root, int64_t f_out, uint32_t flags, double p, float* gx,
-            float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes, cudaStream_t s);
+            const uint8_t* mask_bits, float* h, float* y, uint32_t* actmask, void* ws_ptr, int64_t ws_bytes,
+            cudaStream_t s, const uint64_t* offset_ptr);
+int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y,
+            const uint32_t* actmask, const float* gy, int64_t f_in, const float* w, const float* root, int64_t f_out,
+            uint32_t flags, double p, float* gx, float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes,
+            cudaStream_t s);
 int launch_logsoftmax_nll(const float* logits, int64_t n, int64_t c, const int64_t* idx, const int64_t* y,
                           int64_t n_idx, float* logp, float* loss, float* glogits, void* ws, int64_t ws_bytes,
                           cudaStream_t s);
@@ -198,7 +199,7 @@ static int trainer_forward(Trainer* t, bool train, cudaStream_t s) {
     if (train && t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
     MPGNN_PROPAGATE(hop_fwd(t->g, t->rel[k], in, fi, t->params + t->off_w[k], t->params + t->off_root[k],
                             t->params + t->off_bias[k], H, fl, t->dropout_p, t->seed, 0, nullptr, t->h[k], t->y[k],
-                            t->ws, t->ws_bytes, s, &t->st->drop_off[k]));
+                            nullptr, t->ws, t->ws_bytes, s, &t->st->drop_off[k]));
     in = t->y[k];
   }
   GemmRowsArgs a{};
@@ -255,7 +256,7 @@ static int trainer_backward(Trainer* t, cudaStream_t s) {
     uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16));
     if (t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
     if (k > 0) fl |= MPGNN_F_NEED_GX;
-    MPGNN_PROPAGATE(hop_bwd(t->g, t->rel[k], in, t->h[k], t->y[k], gy, fi, t->params + t->off_w[k],
+    MPGNN_PROPAGATE(hop_bwd(t->g, t->rel[k], in, t->h[k], t->y[k], nullptr, gy, fi, t->params + t->off_w[k],
                             t->params + t->off_root[k], H, fl, t->dropout_p, k > 0 ? gx : nullptr,
                             t->grads + t->off_w[k], t->grads + t->off_root[k], t->grads + t->off_bias[k], t->ws,
                             t->ws_bytes, s));

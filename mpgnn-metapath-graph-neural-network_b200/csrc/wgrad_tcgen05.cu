@@ -43,6 +43,7 @@ struct ParamsW {
   int64_t m; int64_t rows_per_cta;
   float* partials;       // [grid][2][128][n]
   float* colsum_part;    // [grid][32][n]
+  const uint32_t* b_actmask; float b_scale;   // B(r,c) := bit(r,c) ? B(r,c)*b_scale : 0 ([m][n/32] words) or null
 };
 
 // instruction descriptor: fp32 accumulate, tf32 x tf32, A and B both MN-major
@@ -70,9 +71,9 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t sbo) {
   return d;
 }
 
+template <int N, bool kMasked>     // N = width of B (64 or 128); kMasked: B is gated by the activation bitmask
 __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int N = p.n;
   const int b_tile_bytes = kRowsPerChunk * N * 4;                    // one of hi / lo
   const int stage_bytes = 4 * kATileBytes + 2 * b_tile_bytes;        // a1 hi/lo, a2 hi/lo, b hi/lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * stage_bytes);
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
     // a warp instruction moves whole node rows: 32 lanes x 16 bytes = one 512-byte row (N = 128) or two
     // 256-byte rows (N = 64): fully coalesced loads; the swizzled destination keeps each quarter-warp
     // inside one 128-byte line, so the stores are conflict free.
-    const int n_units_b = kRowsPerChunk * N / 4 / kProducerThreadsW;   // 2 (N=128) or 1 (N=64)
-    const int b_atoms = N / 32;
+    constexpr int n_units_b = kRowsPerChunk * N / 4 / kProducerThreadsW;   // 2 (N=128) or 1 (N=64)
+    constexpr int b_atoms = N / 32;
     int a_row[2], a_col[2], a_soff[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -137,8 +138,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
     }
     float4 csum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     float4 buf[2][6];
+    uint32_t mbuf[2][2] = {{0u, 0u}, {0u, 0u}};            // activation-mask words of the B units in flight
+    constexpr bool masked = kMasked;
+    constexpr int b_words = N / 32;
     int pf = 0;                                            // next chunk to prefetch
-    auto issue = [&](float4 (&dst)[6]) {
+    auto issue = [&](float4 (&dst)[6], uint32_t (&mw)[2]) {
       const int64_t row0 = r_begin + (int64_t)pf * kRowsPerChunk;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
         dst[2 + u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
         const int64_t rb = row0 + b_row[u];
         dst[4 + u] = (u < n_units_b && rb < r_end) ? __ldg(reinterpret_cast<const float4*>(p.b + rb * p.ldb + b_col[u])) : z;
+        if (masked) mw[u] = (u < n_units_b && rb < r_end) ? __ldg(p.b_actmask + rb * b_words + (b_col[u] >> 5)) : 0u;
       }
       ++pf;
     };
@@ -158,20 +163,28 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
       *reinterpret_cast<float4*>(hi_ptr) = h;
       *reinterpret_cast<float4*>(hi_ptr + lo_delta) = l;
     };
-    auto store = [&](int s, const float4 (&src)[6]) {
+    auto store = [&](int s, const float4 (&src)[6], const uint32_t (&mw)[2]) {
       uint8_t* st = smem + (size_t)s * stage_bytes;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         split_store(st + a_soff[u], kATileBytes, src[u]);                         // a1: hi @0, lo @16K
         split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
         if (u < n_units_b) {
-          split_store(st + 4 * kATileBytes + b_soff[u], b_tile_bytes, src[4 + u]);  // b: hi, lo
-          csum[u].x += src[4 + u].x; csum[u].y += src[4 + u].y; csum[u].z += src[4 + u].z; csum[u].w += src[4 + u].w;
+          float4 b = src[4 + u];
+          if (masked) {                                   // fused ReLU/dropout backward: g_z = g_y gated by [y > 0]
+            const uint32_t nib = mw[u] >> (b_col[u] & 31);
+            b.x = (nib & 1u) ? b.x * p.b_scale : 0.f;
+            b.y = (nib & 2u) ? b.y * p.b_scale : 0.f;
+            b.z = (nib & 4u) ? b.z * p.b_scale : 0.f;
+            b.w = (nib & 8u) ? b.w * p.b_scale : 0.f;
+          }
+          split_store(st + 4 * kATileBytes + b_soff[u], b_tile_bytes, b);          // b: hi, lo
+          csum[u].x += b.x; csum[u].y += b.y; csum[u].z += b.z; csum[u].w += b.w;
         }
       }
     };
-    if (0 < n_chunks) issue(buf[0]);
-    if (1 < n_chunks) issue(buf[1]);
+    if (0 < n_chunks) issue(buf[0], mbuf[0]);
+    if (1 < n_chunks) issue(buf[1], mbuf[1]);
     int s = 0;
     uint32_t sph = 0;
     for (int it0 = 0; it0 < n_chunks; it0 += 2) {
@@ -180,11 +193,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
         const int it = it0 + j;
         if (it < n_chunks) {
           mbar_wait(bar_empty + 8 * s, sph ^ 1u);
-          store(s, buf[j]);
+          store(s, buf[j], mbuf[j]);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full + 8 * s);
-          if (it + 2 < n_chunks) issue(buf[j]);
+          if (it + 2 < n_chunks) issue(buf[j], mbuf[j]);
           if (++s == kStagesW) { s = 0; sph ^= 1u; }
         }
       }
@@ -320,13 +333,20 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   p.a2 = a.a2; p.lda2 = a.lda2;
   p.b = a.b; p.ldb = a.ldb; p.n = (int)a.n;
   p.m = a.m; p.rows_per_cta = rpc;
+  p.b_actmask = a.b_actmask; p.b_scale = a.b_scale;
   p.partials = ws;
   p.colsum_part = ws + (int64_t)grid * 2 * tcw::kFeat * a.n;
   const size_t smem = (size_t)tcw::kStagesW * (4 * tcw::kATileBytes + 2 * tcw::kRowsPerChunk * a.n * 4) +
                       (2 * tcw::kStagesW + 1) * 8 + 16;
-  MPGNN_CUDA_CHECK(cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tcw::wgrad_tc_kernel<<<grid, tcw::kThreadsW, smem, s>>>(p);
-  MPGNN_LAUNCH_CHECK();
+  auto launch = [&](auto kernel) -> int {
+    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, tcw::kThreadsW, smem, s>>>(p);
+    MPGNN_LAUNCH_CHECK();
+    return MPGNN_OK;
+  };
+  const bool masked = a.b_actmask != nullptr;
+  if (a.n == 128) MPGNN_PROPAGATE(masked ? launch(tcw::wgrad_tc_kernel<128, true>) : launch(tcw::wgrad_tc_kernel<128, false>));
+  else MPGNN_PROPAGATE(masked ? launch(tcw::wgrad_tc_kernel<64, true>) : launch(tcw::wgrad_tc_kernel<64, false>));
   const int total = 2 * tcw::kFeat * (int)a.n + (int)a.n;
   tcw::wgrad_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(p.partials, p.colsum_part, grid, (int)a.n,
                                                                           a.out1, a.ldo1, a.out2, a.ldo2, a.out_ones);

@@ -54,15 +54,19 @@ class _HopFunction(torch.autograd.Function):
         dev = x.device
         h = torch.empty(n, f_in, dtype=torch.float32, device=dev)
         y = torch.empty(n, f_out, dtype=torch.float32, device=dev)
+        # [y > 0] as a bitmask: all the backward needs of y, at 1/32 of its size
+        actmask = (torch.empty(n, f_out // 32, dtype=torch.int32, device=dev)
+                   if (flags & _lib.F_RELU) and f_out % 32 == 0 else None)
         ws_bytes = lib.mpgnn_hop_workspace_bytes(n, f_in, f_out)
         ws = _workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
             rc = lib.mpgnn_hop_fwd(graph.handle, int(relation), _lib.ptr(x), f_in, _lib.ptr(weight), _lib.ptr(root),
                                    _lib.ptr(bias), f_out, flags, float(dropout_p), int(seed), int(offset),
-                                   _lib.ptr(mask_bits), _lib.ptr(h), _lib.ptr(y), _lib.ptr(ws), ws.numel(),
-                                   _lib.current_stream())
+                                   _lib.ptr(mask_bits), _lib.ptr(h), _lib.ptr(y), _lib.ptr(actmask), _lib.ptr(ws),
+                                   ws.numel(), _lib.current_stream())
         _lib.check(rc)
-        ctx.save_for_backward(x, h, y, weight, root)
+        ctx.use_actmask = actmask is not None
+        ctx.save_for_backward(x, h, actmask if ctx.use_actmask else y, weight, root)
         ctx.graph, ctx.relation, ctx.flags, ctx.dropout_p = graph, int(relation), flags, float(dropout_p)
         ctx.has_bias = bias is not None
         return y
@@ -70,7 +74,8 @@ class _HopFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         lib = _lib.load()
-        x, h, y, weight, root = ctx.saved_tensors
+        x, h, y_or_mask, weight, root = ctx.saved_tensors
+        y, actmask = (None, y_or_mask) if ctx.use_actmask else (y_or_mask, None)
         n, f_in = x.shape
         f_out = weight.size(1)
         dev = x.device
@@ -85,7 +90,7 @@ class _HopFunction(torch.autograd.Function):
         ws = _workspace(dev, ws_bytes)
         with torch.cuda.device(dev):
             rc = lib.mpgnn_hop_bwd(ctx.graph.handle, ctx.relation, _lib.ptr(x), _lib.ptr(h), _lib.ptr(y),
-                                   _lib.ptr(gy), f_in, _lib.ptr(weight), _lib.ptr(root), f_out, flags,
+                                   _lib.ptr(actmask), _lib.ptr(gy), f_in, _lib.ptr(weight), _lib.ptr(root), f_out, flags,
                                    ctx.dropout_p, _lib.ptr(gx), _lib.ptr(gw), _lib.ptr(groot), _lib.ptr(gbias),
                                    _lib.ptr(ws), ws.numel(), _lib.current_stream())
         _lib.check(rc)

@@ -23,7 +23,7 @@ def _graph(n, e, r, seed):
     return torch.randint(0, n, (2, e), generator=g), torch.randint(0, r, (e,), generator=g)
 
 
-def _fwd(graph, rel, x, w, root, b, flags, mask_bits):
+def _fwd(graph, rel, x, w, root, b, flags, mask_bits, actmask=None):
     lib = _lib.load()
     n, f_in = x.shape
     f_out = w.size(1)
@@ -31,20 +31,26 @@ def _fwd(graph, rel, x, w, root, b, flags, mask_bits):
     y = torch.empty(n, f_out, device=DEV)
     ws = torch.empty(lib.mpgnn_hop_workspace_bytes(n, f_in, f_out), dtype=torch.uint8, device=DEV)
     _lib.check(lib.mpgnn_hop_fwd(graph.handle, rel, _lib.ptr(x), f_in, _lib.ptr(w), _lib.ptr(root), _lib.ptr(b), f_out,
-                                 flags, 0.6, 0, 0, _lib.ptr(mask_bits), _lib.ptr(h), _lib.ptr(y), _lib.ptr(ws),
-                                 ws.numel(), _lib.current_stream()))
+                                 flags, 0.6, 0, 0, _lib.ptr(mask_bits), _lib.ptr(h), _lib.ptr(y), _lib.ptr(actmask),
+                                 _lib.ptr(ws), ws.numel(), _lib.current_stream()))
     torch.cuda.synchronize()
     return h, y
 
 
-def _bwd(graph, rel, x, h, y, gy, w, root, flags):
+def _unpack_actmask(words, f_out):
+    """[n, f_out/32] int32 words -> [n, f_out] bool (bit j of word c = column 32c+j)."""
+    sh = torch.arange(32, device=words.device, dtype=torch.int64)
+    return ((words.to(torch.int64).unsqueeze(-1) >> sh) & 1).bool().reshape(words.size(0), f_out)
+
+
+def _bwd(graph, rel, x, h, y, gy, w, root, flags, actmask=None):
     lib = _lib.load()
     n, f_in = x.shape
     f_out = w.size(1)
     gx = torch.empty(n, f_in, device=DEV)
     gw, gr, gb = torch.empty_like(w), torch.empty_like(root), torch.empty(f_out, device=DEV)
     ws = torch.empty(lib.mpgnn_hop_workspace_bytes(n, f_in, f_out), dtype=torch.uint8, device=DEV)
-    _lib.check(lib.mpgnn_hop_bwd(graph.handle, rel, _lib.ptr(x), _lib.ptr(h), _lib.ptr(y), _lib.ptr(gy), f_in,
+    _lib.check(lib.mpgnn_hop_bwd(graph.handle, rel, _lib.ptr(x), _lib.ptr(h), _lib.ptr(y), _lib.ptr(actmask), _lib.ptr(gy), f_in,
                                  _lib.ptr(w), _lib.ptr(root), f_out, flags | _lib.F_NEED_GX, 0.6, _lib.ptr(gx),
                                  _lib.ptr(gw), _lib.ptr(gr), _lib.ptr(gb), _lib.ptr(ws), ws.numel(),
                                  _lib.current_stream()))
@@ -85,6 +91,30 @@ def test_hop_tf32x3_matches_fp32_paths(n, f_in, f_out):
     gx_ref, gw_ref, gr_ref, gb_ref = orc.conv_backward(x, ei, et, 1, w, root, h, cnt, gz)
     for a, c in zip(gtc, (gx_ref, gw_ref, gr_ref, gb_ref)):
         assert rel_err(a, c) < TOL
+
+
+@pytest.mark.parametrize("n,f_in,f_out,tc", [(5000, 128, 128, True), (19001, 128, 64, True), (3000, 64, 64, True),
+                                             (2500, 96, 96, False), (777, 128, 128, False)])
+def test_activation_bitmask_replaces_y_in_the_backward(n, f_in, f_out, tc):
+    """hop_fwd's bitmask == [y > 0]; hop_bwd fed the bitmask (no y, g_z never materialised on the
+    tensor-core path) returns bit-for-bit what the y-based backward returns."""
+    ei, et = _graph(n, 5 * n, 2, seed=n + 7)
+    gen = torch.Generator().manual_seed(n)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 2, device=DEV)
+    x = torch.randn(n, f_in, generator=gen).to(DEV)
+    gy = torch.randn(n, f_out, generator=gen).to(DEV)
+    w = (torch.randn(f_in, f_out, generator=gen) * 0.1).to(DEV)
+    root = (torch.randn(f_in, f_out, generator=gen) * 0.1).to(DEV)
+    b = (torch.randn(f_out, generator=gen) * 0.1).to(DEV)
+    flags = _lib.F_RELU | _lib.F_DROPOUT_SEED | (_lib.F_TF32X3 if tc else 0)
+    am = torch.full((n, f_out // 32), -1, dtype=torch.int32, device=DEV)
+    h, y = _fwd(graph, 1, x, w, root, b, flags, None, actmask=am)
+    assert torch.equal(_unpack_actmask(am, f_out), y > 0)
+    assert 0.1 < float((y > 0).float().mean()) < 0.3          # relu (~half) x keep 0.4
+    ref = _bwd(graph, 1, x, h, y, gy, w, root, flags)
+    got = _bwd(graph, 1, x, h, None, gy, w, root, flags, actmask=am)
+    for a, c in zip(got, ref):
+        assert torch.equal(a, c)
 
 
 def test_hop_tf32x3_seeded_dropout_same_stream_as_fp32():
