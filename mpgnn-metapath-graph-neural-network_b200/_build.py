@@ -18,6 +18,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
+# profiling builds only (e.g. MPGNN_NVCC_EXTRA=-DMPGNN_TC_EXPERIMENT, see scripts/exp_variants.sh)
+NVCC_FLAGS += os.environ.get("MPGNN_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -15,11 +15,14 @@
 //    K-step the shared-memory operand fetch (A 4 KB + B 2-4 KB per MMA at ~110 B/clk) was the
 //    bound, so only the small resident B is read from shared memory now.  One thread streams raw
 //    fp32 A chunks (128 rows x 32 K) with TMA (cp.async.bulk.tensor, SWIZZLE_128B, OOB rows zero
-//    filled) into a 4-deep shared ring; 16 converter warps read their row slice conflict-free (the
-//    swizzle spreads the 8 rows of a quarter-warp over the 8 bank groups), split hi/lo in registers
-//    and tcgen05.st them into a 4-stage ring of TMEM columns (lane = row, column = k).
-//  * one warp issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step, A from TMEM) from
-//    an elected lane into one of two TMEM accumulators and tcgen05.commit's the barriers.
+//    filled) into a 4-deep shared ring; 16 converter warps in two groups that take alternate chunks
+//    (a warp's wait -> LDS -> split -> tcgen05.st -> wait::st -> arrive chain is long, so consecutive
+//    chunks must not be serialised behind one warp) read their 32 rows x 16 K-columns conflict-free
+//    (the swizzle spreads the 8 rows of a quarter-warp over the 8 bank groups), split hi/lo in
+//    registers and tcgen05.st them into a 4-stage ring of TMEM columns (lane = row, column = k).
+//  * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step, A from
+//    TMEM) into one of two TMEM accumulators and tcgen05.commit's the barriers (the stage-free
+//    barrier once per pair of chunks: the serial issue path of this thread is what bounds the kernel).
 //  * 8 epilogue warps (two per TMEM lane quarter, each owning alternate 32-column chunks)
 //    tcgen05.ld the accumulator and hand it back to the MMA warp at once, apply bias / degree
 //    normalisation / relu / dropout in registers (the kernel is specialised on the dropout mode
@@ -40,6 +43,9 @@ constexpr int kChunkK = 32;                       // fp32 elements per pipeline 
 constexpr int kStages = 4;                        // TMEM A stages in flight (64 columns each)
 constexpr int kRawStages = 4;                     // TMA-filled raw fp32 chunks in flight
 constexpr int kProducerWarps = 16;
+constexpr int kConvGroups = 2;                                    // converter groups taking alternate chunks
+constexpr int kConvGroupWarps = kProducerWarps / kConvGroups;     // 8: 4 TMEM lane quarters x 2 halves of the 32 K-columns
+static_assert(kStages == kRawStages && (kStages & (kStages - 1)) == 0 && kStages % kConvGroups == 0, "ring geometry");
 constexpr int kEpiWarps = 8;
 // Warp roles by warp id: producers first, epilogue warps next (id % 4 = TMEM lane quarter;
 // kProducerWarps is a multiple of 4), the single MMA-issuing warp last.
@@ -65,7 +71,23 @@ struct Params {
   float* out; int64_t ldo;
   uint32_t* actmask_out;                       // [m][n/32] words, bit j of word c = [out(row, 32c+j) > 0]
   const uint32_t* a_actmask; float a_scale;    // A(r,k) := bit(r,k) ? A(r,k)*a_scale : 0 ([m][K/32] words, k2 == 0)
+#ifdef MPGNN_TC_EXPERIMENT
+  int exp;   // profiling build only (scripts/exp_variants.sh): bits switch pipeline stages off; results are WRONG
+#endif
 };
+#ifdef MPGNN_TC_EXPERIMENT
+#define TC_EXP(bit) ((p.exp & (bit)) != 0)
+// cycle counters of CTA 0 (one lane per role): [role*8 + k]
+__device__ unsigned long long g_tc_dbg[64];
+#define TC_T0() const long long _t0 = clock64()
+#define TC_ACC(var) var += clock64() - _t0
+#define TC_DUMP(role, k, v) do { if (blockIdx.x == 0 && lane == 0) g_tc_dbg[(role) * 8 + (k)] = (unsigned long long)(v); } while (0)
+#else
+#define TC_EXP(bit) false
+#define TC_T0()
+#define TC_ACC(var)
+#define TC_DUMP(role, k, v)
+#endif
 
 // Re-lays B[K,N] (row-major) into per-slice UMMA images: element (n,k) of a slice lives at byte
 // (n/8)*SBO + (k/4)*128 + (n%8)*16 + (k%4)*4 with SBO = (K/4)*128, split into hi and lo.
@@ -83,7 +105,8 @@ __global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, 
   base[(int64_t)k * bn + off] = v - hi;
 }
 
-template <int kDrop, bool kDeg>      // kDrop: 0 none, 1 seeded, 2 mask bits; kDeg: divide the first deg_cols columns by deg
+// kDrop: 0 none, 1 seeded, 2 mask bits; kDeg: divide the first deg_cols columns by deg; kMasked: gate A by a_actmask
+template <int kDrop, bool kDeg, bool kMasked>
 __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_a1,
                                                                    const __grid_constant__ CUtensorMap tmap_a2,
                                                                    const __grid_constant__ CUtensorMap tmap_out) {
@@ -115,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar_full + 8 * s, kProducerWarps);
+      mbar_init(bar_full + 8 * s, kConvGroupWarps);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -124,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     }
     for (int r = 0; r < kRawStages; ++r) {
       mbar_init(bar_rfull + 8 * r, 1);                 // one arrive.expect_tx + the TMA's byte count
-      mbar_init(bar_rempty + 8 * r, kProducerWarps);
+      mbar_init(bar_rempty + 8 * r, kConvGroupWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -151,62 +174,76 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
 
   if (warp < kProducerWarps) {
     // ================================ A converters (raw smem -> hi/lo -> TMEM) ===========
-    // converter warps: warp w owns TMEM lane quarter w&3 (rows 32*(w&3)+lane) and the 8 K-columns
-    // (w>>2)*8.. of every chunk = two 16-byte pieces of its row in the raw tile.  The tile is laid out by
-    // the TMA with the 128-byte swizzle: piece c of row r sits at r*128 + ((c ^ (r&7)) * 16).
-    const int quarter = warp & 3, colgrp = warp >> 2;
+    // group g = warp/8 takes chunks g, g+2, ...; inside a group warp w owns TMEM lane quarter w&3 (rows
+    // 32*(w&3)+lane) and K-columns 16*((w>>2)&1).. of the chunk = four 16-byte pieces of its row in the raw
+    // tile.  The tile is laid out by the TMA with the 128-byte swizzle: piece c of row r sits at
+    // r*128 + ((c ^ (r&7)) * 16).  Chunk `it` lives in raw stage / TMEM stage it % 4.
+    const int grp = warp / kConvGroupWarps;
+    const int quarter = warp & 3, colhalf = (warp >> 2) & 1;
     const int row = quarter * 32 + lane;
-    const int off0 = row * 128 + (((2 * colgrp) ^ (row & 7)) << 4);
-    const int off1 = row * 128 + (((2 * colgrp + 1) ^ (row & 7)) << 4);
-    const uint32_t my_taddr = tmem_a + (uint32_t)(colgrp * 8) + ((uint32_t)(quarter * 32) << 16);
+    int off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) off[j] = row * 128 + (((4 * colhalf + j) ^ (row & 7)) << 4);
+    const uint32_t my_taddr = tmem_a + (uint32_t)(colhalf * 16) + ((uint32_t)(quarter * 32) << 16);
     const int total = my_tiles * kch;
-    int s = 0, rs = 0;
-    uint32_t sph = 0, rph = 0;      // parities of the current use of TMEM stage s / raw stage rs
     // fused ReLU/dropout backward (dgrad): the operand is g_y gated by the activation bitmask of y;
-    // the 32-bit word of (row, chunk) is fetched one chunk ahead
-    const bool masked = p.a_actmask != nullptr;
-    int mc = 0, mtile = 0;
+    // the 32-bit word of (row, chunk) is fetched one of this warp's chunks ahead
+    int mc = grp, mtile = 0;
     auto load_mask_word = [&]() -> uint32_t {
+      while (mc >= kch) { mc -= kch; ++mtile; }
       const int64_t grow = (int64_t)(group + (int64_t)mtile * n_groups) * kTileM + row;
       const uint32_t w = grow < p.m ? __ldg(p.a_actmask + grow * kch + mc) : 0u;
-      if (++mc == kch) { mc = 0; ++mtile; }
+      mc += kConvGroups;
       return w;
     };
-    uint32_t mw = (masked && total > 0) ? load_mask_word() : 0u;
-    for (int it = 0; it < total; ++it) {
-      const uint8_t* tile = sm_raw + (size_t)rs * kRawBytes;
-      const uint32_t mw_next = (masked && it + 1 < total) ? load_mask_word() : 0u;
-      mbar_wait(bar_rfull + 8 * rs, rph);                       // the TMA bytes of this chunk have landed
-      const float4 v0 = *reinterpret_cast<const float4*>(tile + off0);
-      const float4 v1 = *reinterpret_cast<const float4*>(tile + off1);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);          // raw stage may be refilled
-      float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      if (masked) {
-        const uint32_t bits = mw >> (colgrp * 8);
+    uint32_t mw = (kMasked && grp < total) ? load_mask_word() : 0u;
+    long long c_rfull = 0, c_empty = 0, c_st = 0, c_total = clock64();
+    for (int it = grp; it < total; it += kConvGroups) {
+      const int s = it & (kStages - 1);
+      const uint32_t ph = (uint32_t)(it / kStages) & 1u;       // parity of this use of raw stage s / TMEM stage s
+      const uint8_t* tile = sm_raw + (size_t)s * kRawBytes;
+      const uint32_t mw_next = (kMasked && it + kConvGroups < total) ? load_mask_word() : 0u;
+      { TC_T0(); mbar_wait(bar_rfull + 8 * s, ph); TC_ACC(c_rfull); }   // the TMA bytes of this chunk have landed
+      float vv[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) vv[e] = ((bits >> e) & 1u) ? vv[e] * p.a_scale : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = TC_EXP(2) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(tile + off[j]);
+        vv[4 * j] = v.x; vv[4 * j + 1] = v.y; vv[4 * j + 2] = v.z; vv[4 * j + 3] = v.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_rempty + 8 * s);           // raw stage may be refilled
+      if (kMasked) {
+        const uint32_t bits = mw >> (colhalf * 16);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) vv[e] = ((bits >> e) & 1u) ? vv[e] * p.a_scale : 0.f;
         mw = mw_next;
       }
-      uint32_t hi[8], lo[8];
+      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float h = tf32_hi(vv[e]);
+      for (int e = 0; e < 16; ++e) {
+        const float h = TC_EXP(2) ? vv[e] : tf32_hi(vv[e]);
         hi[e] = __float_as_uint(h);
-        lo[e] = __float_as_uint(vv[e] - h);
+        lo[e] = __float_as_uint(TC_EXP(2) ? vv[e] : vv[e] - h);
       }
       // TMEM stage s (hi columns [0,32), lo columns [32,64)) once the MMAs that read it are done
-      mbar_wait(bar_empty + 8 * s, sph ^ 1u);
-      tc_fence_after();
-      const uint32_t ta = my_taddr + (uint32_t)(s * kACols);
-      tmem_st8(ta, hi);
-      tmem_st8(ta + kChunkK, lo);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * s);
-      if (++s == kStages) { s = 0; sph ^= 1u; }
-      if (++rs == kRawStages) { rs = 0; rph ^= 1u; }
+      { TC_T0(); mbar_wait(bar_empty + 8 * (s >> 1), ph ^ 1u); TC_ACC(c_empty); }   // one barrier per pair of stages
+      {
+        TC_T0();
+        tc_fence_after();
+        const uint32_t ta = my_taddr + (uint32_t)(s * kACols);
+        tmem_st16(ta, hi);
+        tmem_st16(ta + kChunkK, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        TC_ACC(c_st);
+      }
+    }
+    if (warp == 0 || warp == kConvGroupWarps) {
+      const int role = warp == 0 ? 0 : 1;
+      TC_DUMP(role, 0, clock64() - c_total); TC_DUMP(role, 1, c_rfull); TC_DUMP(role, 2, c_empty); TC_DUMP(role, 3, c_st);
+      TC_DUMP(role, 4, total);
     }
   } else if (warp < kMmaWarp) {
     // ================================ epilogue =========================================
@@ -223,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     const uint32_t thr_hi = p.dropout_thr16 << 16;
     uint64_t launch_key = 0;
     if (kDrop == 1) launch_key = dropout_launch_key(p.seed, p.offset + (p.offset_ptr != nullptr ? *p.offset_ptr : 0ull));
+    long long e_tfull = 0, e_ld = 0, e_total = clock64();
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int buf = ti & 1;
       const uint32_t ph = (uint32_t)((ti >> 1) & 1);
@@ -235,17 +273,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       }
       uint64_t row_key = 0;
       if (kDrop == 1) row_key = dropout_row_key(launch_key, (uint64_t)row);
-      mbar_wait(bar_tfull + 8 * buf, ph);
+      { TC_T0(); mbar_wait(bar_tfull + 8 * buf, ph); TC_ACC(e_tfull); }
       tc_fence_after();
       for (int cc = half; cc < n_cc; cc += 2) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + cc * kEpiCols) + ((uint32_t)(quarter * 32) << 16);
-        tmem_ld32(taddr, v);
+        { TC_T0(); tmem_ld32(taddr, v); TC_ACC(e_ld); }
         if (cc + 2 >= n_cc) {        // this warp's last read of the accumulator: hand it back before the math
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
+        if (TC_EXP(1)) continue;
         const int lcol0 = cc * kEpiCols;                    // column inside the slice
         const int col0 = slice * BN + lcol0;                // global output column
         const bool scale_deg = kDeg && col0 < p.deg_cols;   // deg_cols is a multiple of 32 (checked on host)
@@ -293,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
                        : "memory");
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !TC_EXP(16)) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(&tmap_out)),
                        "r"(stg_tile), "r"(col0), "r"((int)(row0 + quarter * 32))
@@ -303,6 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (ew == 0) { TC_DUMP(2, 0, clock64() - e_total); TC_DUMP(2, 1, e_tfull); TC_DUMP(2, 2, e_ld); TC_DUMP(2, 4, my_tiles); }
   } else if (warp == kTmaWarp) {
     // ================================ TMA producer (one lane) ============================
     if (lane == 0) {
@@ -310,8 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       int rs = 0;
       uint32_t rph = 0;
       int tile_i = 0, c = 0;
+      long long t_rempty = 0, t_total = clock64();
       for (int it = 0; it < total; ++it) {
-        mbar_wait(bar_rempty + 8 * rs, rph ^ 1u);             // converters are done with this raw stage
+        { TC_T0(); mbar_wait(bar_rempty + 8 * rs, rph ^ 1u); TC_ACC(t_rempty); }   // converters are done with this raw stage
         const int kbase = c * kChunkK;
         const bool first = kbase < p.k1;
         const CUtensorMap* map = first ? &tmap_a1 : &tmap_a2;
@@ -319,6 +360,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         const int64_t row0 = (int64_t)(group + (int64_t)tile_i * n_groups) * kTileM;
         const uint32_t dst = smem_u32(sm_raw + (size_t)rs * kRawBytes);
         const uint32_t bar = bar_rfull + 8 * rs;
+        if (TC_EXP(8)) {
+          mbar_arrive(bar);
+          if (++c == kch) { c = 0; ++tile_i; }
+          if (++rs == kRawStages) { rs = 0; rph ^= 1u; }
+          continue;
+        }
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kRawBytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -327,24 +374,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         if (++c == kch) { c = 0; ++tile_i; }
         if (++rs == kRawStages) { rs = 0; rph ^= 1u; }
       }
+      TC_DUMP(3, 0, clock64() - t_total); TC_DUMP(3, 1, t_rempty);
     }
   } else {
-    // ================================ MMA issuer (whole warp converged; one elected lane issues) ====
-    const uint32_t idesc = make_idesc(kTileM, BN);
-    const uint32_t b_sbo = (uint32_t)(K / 4) * 128;
-    const uint32_t bh_lo0 = desc_lo(smem_u32(sm_b_hi)), bl_lo0 = desc_lo(smem_u32(sm_b_lo));
-    int s = 0;
-    uint32_t sph = 0;
-    for (int ti = 0; ti < my_tiles; ++ti) {
-      const int buf = ti & 1;
-      const uint32_t ph = (uint32_t)((ti >> 1) & 1);
-      mbar_wait(bar_tempty + 8 * buf, ph ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-      for (int c = 0; c < kch; ++c) {
-        mbar_wait(bar_full + 8 * s, sph);
+    // ================================ MMA issuer ==========================================
+    // ONE elected thread runs the whole loop (the per-chunk elect + reconvergence cost ~100 cycles of the
+    // serial issue path); it commits the "stage free" barrier once per PAIR of chunks: a tcgen05.commit
+    // holds the issuing thread for 130-240 cycles, as long as the MMAs of half a chunk.
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(kTileM, BN);
+      const uint32_t b_sbo = (uint32_t)(K / 4) * 128;
+      const uint32_t bh_lo0 = desc_lo(smem_u32(sm_b_hi)), bl_lo0 = desc_lo(smem_u32(sm_b_lo));
+      int s = 0;
+      uint32_t sph = 0;
+      long long m_tempty = 0, m_full = 0, m_issue = 0, m_total = clock64();
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        const int buf = ti & 1;
+        const uint32_t ph = (uint32_t)((ti >> 1) & 1);
+        { TC_T0(); mbar_wait(bar_tempty + 8 * buf, ph ^ 1u); TC_ACC(m_tempty); }
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int c = 0; c < kch; ++c) {
+          { TC_T0(); mbar_wait(bar_full + 8 * s, sph); TC_ACC(m_full); }
+          tc_fence_after();
+          TC_T0();
           const uint32_t ah = tmem_a + (uint32_t)(s * kACols), al = ah + kChunkK;   // TMEM columns of this stage
           const uint32_t boff = (uint32_t)(c * (kChunkK / 4) * 128) >> 4;
 #pragma unroll
@@ -352,15 +405,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
             const uint64_t dbh = desc_make(bh_lo0 + boff + j * 16, b_sbo);
             const uint64_t dbl = desc_make(bl_lo0 + boff + j * 16, b_sbo);
             umma_tf32_ts(d_tmem, ah + j * 8, dbh, idesc, (c | j) != 0 ? 1u : 0u);
+            if (TC_EXP(4)) continue;
             umma_tf32_ts(d_tmem, al + j * 8, dbh, idesc, 1u);
             umma_tf32_ts(d_tmem, ah + j * 8, dbl, idesc, 1u);
           }
-          umma_commit(bar_empty + 8 * s);       // stage reusable once these MMAs have read it
+          if (s & 1) umma_commit(bar_empty + 8 * (s >> 1));   // stages s-1, s reusable once these MMAs have read them
           if (c == kch - 1) umma_commit(bar_tfull + 8 * buf);   // accumulator complete
+          TC_ACC(m_issue);
+          if (++s == kStages) { s = 0; sph ^= 1u; }
         }
-        __syncwarp();
-        if (++s == kStages) { s = 0; sph ^= 1u; }
       }
+#ifdef MPGNN_TC_EXPERIMENT
+      if (blockIdx.x == 0) {
+        g_tc_dbg[32] = clock64() - m_total; g_tc_dbg[33] = m_tempty; g_tc_dbg[34] = m_full; g_tc_dbg[35] = m_issue;
+      }
+#endif
     }
   }
 
@@ -408,6 +467,12 @@ static int pick_bn(int64_t k, int64_t n) {
   return 0;
 }
 
+#ifdef MPGNN_TC_EXPERIMENT
+extern "C" int mpgnn_tc_debug_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, tc::g_tc_dbg, sizeof(unsigned long long) * 64);
+}
+#endif
+
 int proj_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags) {
   if (!(flags & MPGNN_F_TF32X3)) return 0;   // the bf16 mode is not built yet
   const int64_t k = k1 + k2;
@@ -446,6 +511,9 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits; p.offset_ptr = a.offset_ptr;
   p.out = a.out; p.ldo = a.ldo;
   p.actmask_out = a.actmask_out; p.a_actmask = a.a1_actmask; p.a_scale = a.a1_scale;
+#ifdef MPGNN_TC_EXPERIMENT
+  p.exp = getenv("MPGNN_TC_EXP") ? atoi(getenv("MPGNN_TC_EXP")) : 0;
+#endif
   const int64_t n_tiles = ceil_div(a.m, tc::kTileM);
   int64_t grid = n_tiles * n_slices;
   if (grid > kNumSMs) grid = (kNumSMs / n_slices) * n_slices;
@@ -464,13 +532,17 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
     return MPGNN_OK;
   };
   const bool deg = p.deg_ptr != nullptr && p.deg_cols > 0;
+  if (p.a_actmask != nullptr) {
+    MPGNN_REQUIRE(p.dropout_mode == 0, MPGNN_ENOTSUP, "proj_tcgen05: operand mask with a dropout epilogue");
+    return deg ? launch(tc::gemm_rows_tc_kernel<0, true, true>) : launch(tc::gemm_rows_tc_kernel<0, false, true>);
+  }
   switch (p.dropout_mode * 2 + (deg ? 1 : 0)) {
-    case 0: return launch(tc::gemm_rows_tc_kernel<0, false>);
-    case 1: return launch(tc::gemm_rows_tc_kernel<0, true>);
-    case 2: return launch(tc::gemm_rows_tc_kernel<1, false>);
-    case 3: return launch(tc::gemm_rows_tc_kernel<1, true>);
-    case 4: return launch(tc::gemm_rows_tc_kernel<2, false>);
-    default: return launch(tc::gemm_rows_tc_kernel<2, true>);
+    case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false>);
+    case 1: return launch(tc::gemm_rows_tc_kernel<0, true, false>);
+    case 2: return launch(tc::gemm_rows_tc_kernel<1, false, false>);
+    case 3: return launch(tc::gemm_rows_tc_kernel<1, true, false>);
+    case 4: return launch(tc::gemm_rows_tc_kernel<2, false, false>);
+    default: return launch(tc::gemm_rows_tc_kernel<2, true, false>);
   }
 }
 

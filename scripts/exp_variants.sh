@@ -1,11 +1,8 @@
 #!/bin/bash
-# builds variants of proj_tcgen05.cu by sed-editing constants into a temp copy, timing each
-SRC=mpgnn-metapath-graph-neural-network_b200/csrc/proj_tcgen05.cu
-cp $SRC /tmp/proj_orig.cu
-run() { python mpgnn-metapath-graph-neural-network_b200/_build.py > /dev/null 2>&1 && EXP_TAG="$1" timeout 300 python scripts/exp_tc.py 2>&1 | tail -1; }
-run "base(prefetch4)"
-sed -i 's/constexpr int kPrefetch = 4;/constexpr int kPrefetch = 2;/' $SRC; run "prefetch2"
-cp /tmp/proj_orig.cu $SRC
-sed -i 's/constexpr int kPrefetch = 4;/constexpr int kPrefetch = 6;/' $SRC; run "prefetch6"
-cp /tmp/proj_orig.cu $SRC
-python mpgnn-metapath-graph-neural-network_b200/_build.py > /dev/null 2>&1
+# Pipeline-stage ablation of the tcgen05 projection kernel.  Needs a library built with
+#   MPGNN_NVCC_EXTRA=-DMPGNN_TC_EXPERIMENT python -c "import __graft_entry__ as g; g.build()"
+# MPGNN_TC_EXP bits: 1 epilogue off (ld + release only), 2 converter math/LDS off, 4 only the hi*hi MMA,
+# 8 no TMA loads, 16 no TMA stores.  Results are WRONG by construction; only the times matter.
+for v in 0 1 2 4 8 16 3 11 7 15; do
+  MPGNN_TC_EXP=$v EXP_TAG="exp=$v" timeout 300 python scripts/exp_tc.py 2>&1 | tail -1
+done
