@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmpgnn_b200.so")
+# MPGNN_B200_LIB: an alternative build of the same library (profiling / ablation builds only)
+LIB_PATH = os.environ.get("MPGNN_B200_LIB") or os.path.join(HERE, "libmpgnn_b200.so")
 
 OK, EINVAL, ECUDA, ERANGE, ENOTSUP = 0, -1, -2, -3, -4
 F_RELU, F_DROPOUT_SEED, F_DROPOUT_MASK, F_NEED_GX, F_TF32X3, F_BF16 = 1, 2, 4, 8, 16, 32

@@ -43,6 +43,7 @@ constexpr int kChunkK = 32;                       // fp32 elements per pipeline 
 constexpr int kStages = 4;                        // TMEM A stages in flight (64 columns each)
 constexpr int kRawStages = 4;                     // TMA-filled raw fp32 chunks in flight
 constexpr int kProducerWarps = 16;
+constexpr int kPairShift = 1;                                     // stage-free barrier shared by 2^kPairShift stages
 constexpr int kConvGroups = 2;                                    // converter groups taking alternate chunks
 constexpr int kConvGroupWarps = kProducerWarps / kConvGroups;     // 8: 4 TMEM lane quarters x 2 halves of the 32 K-columns
 static_assert(kStages == kRawStages && (kStages & (kStages - 1)) == 0 && kStages % kConvGroups == 0, "ring geometry");
@@ -77,13 +78,18 @@ struct Params {
 };
 #ifdef MPGNN_TC_EXPERIMENT
 #define TC_EXP(bit) ((p.exp & (bit)) != 0)
+#else
+#define TC_EXP(bit) false
+#endif
+#ifdef MPGNN_TC_COUNTERS
 // cycle counters of CTA 0 (one lane per role): [role*8 + k]
 __device__ unsigned long long g_tc_dbg[64];
+#define TC_NOW() clock64()
 #define TC_T0() const long long _t0 = clock64()
 #define TC_ACC(var) var += clock64() - _t0
 #define TC_DUMP(role, k, v) do { if (blockIdx.x == 0 && lane == 0) g_tc_dbg[(role) * 8 + (k)] = (unsigned long long)(v); } while (0)
 #else
-#define TC_EXP(bit) false
+#define TC_NOW() 0ll
 #define TC_T0()
 #define TC_ACC(var)
 #define TC_DUMP(role, k, v)
@@ -197,21 +203,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       return w;
     };
     uint32_t mw = (kMasked && grp < total) ? load_mask_word() : 0u;
-    long long c_rfull = 0, c_empty = 0, c_st = 0, c_total = clock64();
+    long long c_rfull = 0, c_empty = 0, c_st = 0, c_total = TC_NOW();
     for (int it = grp; it < total; it += kConvGroups) {
       const int s = it & (kStages - 1);
       const uint32_t ph = (uint32_t)(it / kStages) & 1u;       // parity of this use of raw stage s / TMEM stage s
       const uint8_t* tile = sm_raw + (size_t)s * kRawBytes;
       const uint32_t mw_next = (kMasked && it + kConvGroups < total) ? load_mask_word() : 0u;
       { TC_T0(); mbar_wait(bar_rfull + 8 * s, ph); TC_ACC(c_rfull); }   // the TMA bytes of this chunk have landed
+      if (TC_EXP(64)) __nanosleep(500);
       float vv[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 v = TC_EXP(2) ? make_float4(1.f, 2.f, 3.f, 4.f) : *reinterpret_cast<const float4*>(tile + off[j]);
         vv[4 * j] = v.x; vv[4 * j + 1] = v.y; vv[4 * j + 2] = v.z; vv[4 * j + 3] = v.w;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_rempty + 8 * s);           // raw stage may be refilled
+      // The refill of this raw stage is an async-proxy write (TMA) and the reads above are generic-proxy
+      // loads that may still be in flight when a plain arrive is issued (nothing has consumed their
+      // registers yet); the TMA data of the next chunk then lands under them -- seen as a few rows per
+      // million picking up 16-byte pieces of the wrong chunk.  So the arrive is made data-dependent on
+      // one register of each of the four loads of every lane (cheaper than a proxy fence per chunk).
+      uint32_t dep = __float_as_uint(vv[0]) | __float_as_uint(vv[4]) | __float_as_uint(vv[8]) | __float_as_uint(vv[12]);
+      dep = __reduce_or_sync(0xFFFFFFFFu, dep);
+      if (lane == 0) mbar_arrive_after(bar_rempty + 8 * s, dep);   // raw stage may be refilled
       if (kMasked) {
         const uint32_t bits = mw >> (colhalf * 16);
 #pragma unroll
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         lo[e] = __float_as_uint(TC_EXP(2) ? vv[e] : vv[e] - h);
       }
       // TMEM stage s (hi columns [0,32), lo columns [32,64)) once the MMAs that read it are done
-      { TC_T0(); mbar_wait(bar_empty + 8 * (s >> 1), ph ^ 1u); TC_ACC(c_empty); }   // one barrier per pair of stages
+      { TC_T0(); mbar_wait(bar_empty + 8 * (s >> kPairShift), ph ^ 1u); TC_ACC(c_empty); }   // one barrier per pair of stages
       {
         TC_T0();
         tc_fence_after();
@@ -235,14 +248,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         tmem_st16(ta + kChunkK, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        __syncwarp();
+        if (TC_EXP(32)) __nanosleep(500);
+          __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * s);
         TC_ACC(c_st);
       }
     }
     if (warp == 0 || warp == kConvGroupWarps) {
       const int role = warp == 0 ? 0 : 1;
-      TC_DUMP(role, 0, clock64() - c_total); TC_DUMP(role, 1, c_rfull); TC_DUMP(role, 2, c_empty); TC_DUMP(role, 3, c_st);
+      TC_DUMP(role, 0, TC_NOW() - c_total); TC_DUMP(role, 1, c_rfull); TC_DUMP(role, 2, c_empty); TC_DUMP(role, 3, c_st);
       TC_DUMP(role, 4, total);
     }
   } else if (warp < kMmaWarp) {
@@ -260,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     const uint32_t thr_hi = p.dropout_thr16 << 16;
     uint64_t launch_key = 0;
     if (kDrop == 1) launch_key = dropout_launch_key(p.seed, p.offset + (p.offset_ptr != nullptr ? *p.offset_ptr : 0ull));
-    long long e_tfull = 0, e_ld = 0, e_total = clock64();
+    long long e_tfull = 0, e_ld = 0, e_total = TC_NOW();
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int buf = ti & 1;
       const uint32_t ph = (uint32_t)((ti >> 1) & 1);
@@ -274,12 +288,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       uint64_t row_key = 0;
       if (kDrop == 1) row_key = dropout_row_key(launch_key, (uint64_t)row);
       { TC_T0(); mbar_wait(bar_tfull + 8 * buf, ph); TC_ACC(e_tfull); }
+      if (TC_EXP(128)) __nanosleep(500);
       tc_fence_after();
       for (int cc = half; cc < n_cc; cc += 2) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (uint32_t)(buf * BN + cc * kEpiCols) + ((uint32_t)(quarter * 32) << 16);
         { TC_T0(); tmem_ld32(taddr, v); TC_ACC(e_ld); }
-        if (cc + 2 >= n_cc) {        // this warp's last read of the accumulator: hand it back before the math
+        const bool last_read = cc + 2 >= n_cc;   // this warp's last read of the accumulator
+        if (last_read) {                         // hand the accumulator back before the math
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (ew == 0) { TC_DUMP(2, 0, clock64() - e_total); TC_DUMP(2, 1, e_tfull); TC_DUMP(2, 2, e_ld); TC_DUMP(2, 4, my_tiles); }
+    if (ew == 0) { TC_DUMP(2, 0, TC_NOW() - e_total); TC_DUMP(2, 1, e_tfull); TC_DUMP(2, 2, e_ld); TC_DUMP(2, 4, my_tiles); }
   } else if (warp == kTmaWarp) {
     // ================================ TMA producer (one lane) ============================
     if (lane == 0) {
@@ -350,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       int rs = 0;
       uint32_t rph = 0;
       int tile_i = 0, c = 0;
-      long long t_rempty = 0, t_total = clock64();
+      long long t_rempty = 0, t_total = TC_NOW();
       for (int it = 0; it < total; ++it) {
         { TC_T0(); mbar_wait(bar_rempty + 8 * rs, rph ^ 1u); TC_ACC(t_rempty); }   // converters are done with this raw stage
         const int kbase = c * kChunkK;
@@ -374,8 +390,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         if (++c == kch) { c = 0; ++tile_i; }
         if (++rs == kRawStages) { rs = 0; rph ^= 1u; }
       }
-      TC_DUMP(3, 0, clock64() - t_total); TC_DUMP(3, 1, t_rempty);
+      TC_DUMP(3, 0, TC_NOW() - t_total); TC_DUMP(3, 1, t_rempty);
     }
+    __syncwarp();
   } else {
     // ================================ MMA issuer ==========================================
     // ONE elected thread runs the whole loop (the per-chunk elect + reconvergence cost ~100 cycles of the
@@ -387,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       const uint32_t bh_lo0 = desc_lo(smem_u32(sm_b_hi)), bl_lo0 = desc_lo(smem_u32(sm_b_lo));
       int s = 0;
       uint32_t sph = 0;
-      long long m_tempty = 0, m_full = 0, m_issue = 0, m_total = clock64();
+      long long m_tempty = 0, m_full = 0, m_issue = 0, m_total = TC_NOW();
       for (int ti = 0; ti < my_tiles; ++ti) {
         const int buf = ti & 1;
         const uint32_t ph = (uint32_t)((ti >> 1) & 1);
@@ -396,7 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
         for (int c = 0; c < kch; ++c) {
           { TC_T0(); mbar_wait(bar_full + 8 * s, sph); TC_ACC(m_full); }
-          tc_fence_after();
+          if (TC_EXP(256)) __nanosleep(500);
+              tc_fence_after();
           TC_T0();
           const uint32_t ah = tmem_a + (uint32_t)(s * kACols), al = ah + kChunkK;   // TMEM columns of this stage
           const uint32_t boff = (uint32_t)(c * (kChunkK / 4) * 128) >> 4;
@@ -409,18 +427,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
             umma_tf32_ts(d_tmem, al + j * 8, dbh, idesc, 1u);
             umma_tf32_ts(d_tmem, ah + j * 8, dbl, idesc, 1u);
           }
-          if (s & 1) umma_commit(bar_empty + 8 * (s >> 1));   // stages s-1, s reusable once these MMAs have read them
+          if (kPairShift == 0 || (s & 1)) umma_commit(bar_empty + 8 * (s >> kPairShift));   // stages s-1, s reusable once these MMAs have read them
           if (c == kch - 1) umma_commit(bar_tfull + 8 * buf);   // accumulator complete
           TC_ACC(m_issue);
           if (++s == kStages) { s = 0; sph ^= 1u; }
         }
       }
-#ifdef MPGNN_TC_EXPERIMENT
+#ifdef MPGNN_TC_COUNTERS
       if (blockIdx.x == 0) {
         g_tc_dbg[32] = clock64() - m_total; g_tc_dbg[33] = m_tempty; g_tc_dbg[34] = m_full; g_tc_dbg[35] = m_issue;
       }
 #endif
     }
+    __syncwarp();     // the idle lanes must not reach the teardown barrier (and the TMEM dealloc) ahead of the issuer
   }
 
   tc_fence_before();
@@ -467,7 +486,7 @@ static int pick_bn(int64_t k, int64_t n) {
   return 0;
 }
 
-#ifdef MPGNN_TC_EXPERIMENT
+#ifdef MPGNN_TC_COUNTERS
 extern "C" int mpgnn_tc_debug_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, tc::g_tc_dbg, sizeof(unsigned long long) * 64);
 }

@@ -15,6 +15,23 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive that cannot be issued before `dep` has been produced: the barrier address is formed from
+// dep & (dep-1) & 1 (always 0, but opaque to the assembler), so loads feeding `dep` have returned
+// their data when the arrive is performed.  Used where the arrive hands a buffer that generic-proxy
+// loads were reading to an async-proxy writer (TMA): a plain arrive may overtake loads in flight.
+__device__ __forceinline__ void mbar_arrive_after(uint32_t bar, uint32_t dep) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 t;\n\t"
+      "sub.u32 t, %1, 1;\n\t"
+      "and.b32 t, t, %1;\n\t"
+      "and.b32 t, t, 1;\n\t"
+      "shl.b32 t, t, 3;\n\t"
+      "add.u32 t, t, %0;\n\t"
+      "mbarrier.arrive.shared::cta.b64 _, [t];\n\t"
+      "}" ::"r"(bar), "r"(dep)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"

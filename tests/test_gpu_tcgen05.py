@@ -147,3 +147,29 @@ def test_tf32x3_accuracy_is_fp32_class():
         ref = (h / cnt.clamp(min=1).unsqueeze(1)) @ conv.weight.double() + x.double() @ conv.root.double() \
             + conv.bias.double()
     assert rel_err(y, ref) < 2e-6
+
+
+@pytest.mark.parametrize("n,f_in,f_out", [(400000, 64, 64), (200000, 32, 192), (150000, 96, 192), (100000, 128, 128)])
+def test_projection_pipeline_is_race_free_exact_operand_check(n, f_in, f_out):
+    """Stress for the TMA -> converter -> TMEM -> MMA handoffs.  With integer features, W = 0 and root a
+    0/1 selection matrix, y must equal x (column c of y = column c % f_in of x) EXACTLY: the tf32 hi part
+    carries the integer and lo is zero, so any row that picks up a piece of another chunk (a stage reused
+    before its readers were done, seen once as a missing proxy fence) shows up bit-for-bit.  Repeated, since
+    such races hit a few rows per million."""
+    ei, et = _graph(n, 3 * n, 2, seed=n)
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randint(-8, 9, (n, f_in), generator=gen).float().to(DEV)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 2, device=DEV)
+    sel = torch.zeros(f_in, f_out, device=DEV)
+    sel[torch.arange(f_out, device=DEV) % f_in, torch.arange(f_out, device=DEV)] = 1.0
+    zero = torch.zeros(f_in, f_out, device=DEV)
+    b = torch.zeros(f_out, device=DEV)
+    want_x = x[:, torch.arange(f_out, device=DEV) % f_in]
+    for trial in range(6):
+        _, y = _fwd(graph, 1, x, zero, sel, b, _lib.F_TF32X3, None)
+        assert torch.equal(y, want_x), "x operand corrupted in trial %d: %d rows" % (trial, int((y != want_x).any(1).sum()))
+    h, _ = _fwd(graph, 1, x, zero, sel, b, 0, None)
+    want_h = h[:, torch.arange(f_out, device=DEV) % f_in]
+    for trial in range(6):
+        _, y = _fwd(graph, 1, x, sel, zero, b, _lib.F_TF32X3, None)
+        assert float((y - want_h).abs().max()) <= 1e-5 * 8, "h operand corrupted in trial %d" % trial
