@@ -1,6 +1,8 @@
 // extern "C" surface declared in include/mpgnn_b200.h.
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace mpgnn {
@@ -15,8 +17,8 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---- launch counter + optional event timing ------------------------------------------------
-static long long g_launches = 0;
-void count_launch() { ++g_launches; }
+static std::atomic<long long> g_launches{0};   // candidate trainers launch from several host threads
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 constexpr int kMaxTimerSlots = 32;
 constexpr int kMaxTimerEvents = 4096;
@@ -128,7 +130,7 @@ const char* mpgnn_last_error(void) { return g_error; }
 
 int mpgnn_abi_version(void) { return 1; }
 
-long long mpgnn_launch_count(void) { return g_launches; }
+long long mpgnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 void mpgnn_timing_enable(int on) {
   timing_flush();

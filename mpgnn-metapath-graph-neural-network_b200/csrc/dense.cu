@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
 
   const float scale = a.dropout_mode ? a.dropout_scale : 1.f;
   const uint64_t drop_off = a.offset + (a.offset_ptr != nullptr ? *a.offset_ptr : 0ull);
+  const uint64_t launch_key = a.dropout_mode == 1 ? dropout_launch_key(a.seed, drop_off) : 0ull;
   const int64_t mask_ld = (a.n + 7) / 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -76,6 +77,9 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
       const int d = __ldg(a.deg_ptr + row + 1) - __ldg(a.deg_ptr + row);
       inv_deg_den = (float)max(d, 1);
     }
+    // the thread's 4 columns are one aligned block of the dropout stream: one block word per row
+    uint2 dw = make_uint2(0u, 0u);
+    if (a.dropout_mode == 1) dw = dropout_block(dropout_row_key(launch_key, (uint64_t)row), (uint32_t)((col0 + tx * 4) >> 2));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int64_t col = col0 + tx * 4 + j;
@@ -86,7 +90,8 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
       if (a.relu) v = fmaxf(v, 0.f);
       if (a.gate != nullptr) v = (__ldg(a.gate + row * a.ldgate + col) > 0.f) ? v : 0.f;
       if (a.dropout_mode == 1) {
-        v = dropout_keep(a.seed, drop_off, (uint64_t)row, (uint64_t)col, a.dropout_thr16) ? v * scale : 0.f;
+        const uint32_t half = (j & 2) ? dw.y : dw.x;
+        v = ((half >> (16 * (j & 1))) & 0xFFFFu) >= a.dropout_thr16 ? v * scale : 0.f;
       } else if (a.dropout_mode == 2) {
         const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
         v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;

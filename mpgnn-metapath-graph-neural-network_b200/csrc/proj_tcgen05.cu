@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         if (last_read) {                         // hand the accumulator back before the math
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          // data-dependent on the loaded registers: the MMA warp overwrites the accumulator as soon as the
+          // barrier flips, so the LDTM must have delivered (see mbar_arrive_after)
+          if (lane == 0) mbar_arrive_after(bar_tempty + 8 * buf, v[0] | v[31]);
         }
         if (TC_EXP(1)) continue;
         const int lcol0 = cc * kEpiCols;                    // column inside the slice

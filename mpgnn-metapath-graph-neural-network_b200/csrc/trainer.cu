@@ -89,6 +89,7 @@ struct Trainer {
   int64_t off_w[8], off_root[8], off_bias[8], off_w1, off_b1, off_w2, off_b2;
   float *params, *grads, *adam_m, *adam_v;
   float *h[8], *y[8];           // aggregated inputs and activations per layer
+  float* am[8];                 // activation bitmasks [y > 0] (uint32 words) when hidden % 32 == 0, else null
   float *gxa, *gxb;             // ping-pong activation gradients
   float *a1, *lg, *logp, *glg, *gz1, *packed;
   float *loss_train, *loss_val;
@@ -126,6 +127,7 @@ void trainer_free(Trainer* t) {
   for (int k = 0; k < 8; ++k) {
     cudaFree(t->h[k]);
     cudaFree(t->y[k]);
+    cudaFree(t->am[k]);
   }
   cudaFree(t->f1_train); cudaFree(t->f1_val); cudaFree(t->trace); cudaFree(t->cm); cudaFree(t->st); cudaFree(t->ws);
   delete t;
@@ -169,6 +171,7 @@ int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int6
   for (int k = 0; k < n_layers; ++k) {
     TR_ALLOC(t->h[k], n * (k == 0 ? f_in : hidden));
     TR_ALLOC(t->y[k], n * hidden);
+    if (hidden % 32 == 0) TR_ALLOC(t->am[k], n * (hidden / 32));
   }
   TR_ALLOC(t->gxa, n * hidden); TR_ALLOC(t->gxb, n * hidden);
   TR_ALLOC(t->a1, n * hidden); TR_ALLOC(t->lg, n * classes); TR_ALLOC(t->logp, n * classes);
@@ -199,7 +202,8 @@ static int trainer_forward(Trainer* t, bool train, cudaStream_t s) {
     if (train && t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
     MPGNN_PROPAGATE(hop_fwd(t->g, t->rel[k], in, fi, t->params + t->off_w[k], t->params + t->off_root[k],
                             t->params + t->off_bias[k], H, fl, t->dropout_p, t->seed, 0, nullptr, t->h[k], t->y[k],
-                            nullptr, t->ws, t->ws_bytes, s, &t->st->drop_off[k]));
+                            train ? reinterpret_cast<uint32_t*>(t->am[k]) : nullptr, t->ws, t->ws_bytes, s,
+                            &t->st->drop_off[k]));
     in = t->y[k];
   }
   GemmRowsArgs a{};
@@ -256,7 +260,7 @@ static int trainer_backward(Trainer* t, cudaStream_t s) {
     uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16));
     if (t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
     if (k > 0) fl |= MPGNN_F_NEED_GX;
-    MPGNN_PROPAGATE(hop_bwd(t->g, t->rel[k], in, t->h[k], t->y[k], nullptr, gy, fi, t->params + t->off_w[k],
+    MPGNN_PROPAGATE(hop_bwd(t->g, t->rel[k], in, t->h[k], t->y[k], reinterpret_cast<const uint32_t*>(t->am[k]), gy, fi, t->params + t->off_w[k],
                             t->params + t->off_root[k], H, fl, t->dropout_p, k > 0 ? gx : nullptr,
                             t->grads + t->off_w[k], t->grads + t->off_root[k], t->grads + t->off_bias[k], t->ws,
                             t->ws_bytes, s));

@@ -8,6 +8,10 @@
 // both operands are "MN-major" as they sit in HBM (features contiguous).  Same 3xTF32 split as
 // the projection kernel (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulate in TMEM).
 //
+// Narrow inputs (A1, A2 64 wide -- the hidden-64 models of the candidate trainer): the two operands are
+// STACKED along the MMA M dimension into one 128-wide tile ([h | x] per node row), so one accumulator
+// and three MMAs per K-step produce both gradients (rows 0-63 = A1^T B, rows 64-127 = A2^T B).
+//
 // One persistent CTA per SM owns a contiguous range of rows (a fixed function of M, so the
 // summation tree is the same on every run and GPU count) and keeps BOTH 128xN accumulators in
 // TMEM for its whole range; at the end it writes one partial per CTA and a second kernel adds
@@ -71,7 +75,9 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t sbo) {
   return d;
 }
 
-template <int N, bool kMasked>     // N = width of B (64 or 128); kMasked: B is gated by the activation bitmask
+// N = width of B (64 or 128); kMasked: B is gated by the activation bitmask; kStacked: A1, A2 are 64 wide and share
+// one 128-wide operand tile / one accumulator
+template <int N, bool kMasked, bool kStacked>
 __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b_tile_bytes = kRowsPerChunk * N * 4;                    // one of hi / lo
@@ -149,8 +155,14 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
       for (int u = 0; u < 2; ++u) {
         const int64_t ra = row0 + a_row[u];
         const bool ok = ra < r_end;
-        dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a1 + ra * p.lda1 + a_col[u])) : z;
-        dst[2 + u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
+        if (kStacked) {      // [A1 row | A2 row]: lanes 0-15 fetch the 64 floats of A1, lanes 16-31 those of A2
+          const float* src = lane < 16 ? p.a1 + ra * p.lda1 + a_col[u] : p.a2 + ra * p.lda2 + (a_col[u] - 64);
+          dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(src)) : z;
+          dst[2 + u] = z;
+        } else {
+          dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a1 + ra * p.lda1 + a_col[u])) : z;
+          dst[2 + u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
+        }
         const int64_t rb = row0 + b_row[u];
         dst[4 + u] = (u < n_units_b && rb < r_end) ? __ldg(reinterpret_cast<const float4*>(p.b + rb * p.ldb + b_col[u])) : z;
         if (masked) mw[u] = (u < n_units_b && rb < r_end) ? __ldg(p.b_actmask + rb * b_words + (b_col[u] >> 5)) : 0u;
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         split_store(st + a_soff[u], kATileBytes, src[u]);                         // a1: hi @0, lo @16K
-        split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
+        if (!kStacked) split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
         if (u < n_units_b) {
           float4 b = src[4 + u];
           if (masked) {                                   // fused ReLU/dropout backward: g_z = g_y gated by [y > 0]
@@ -232,9 +244,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
           umma_tf32(tmem_base, a1h, bh, idesc, acc);
           umma_tf32(tmem_base, a1l, bh, idesc, 1u);
           umma_tf32(tmem_base, a1h, bl, idesc, 1u);
-          umma_tf32(tmem_base + (uint32_t)N, a2h, bh, idesc, acc);
-          umma_tf32(tmem_base + (uint32_t)N, a2l, bh, idesc, 1u);
-          umma_tf32(tmem_base + (uint32_t)N, a2h, bl, idesc, 1u);
+          if (!kStacked) {
+            umma_tf32(tmem_base + (uint32_t)N, a2h, bh, idesc, acc);
+            umma_tf32(tmem_base + (uint32_t)N, a2l, bh, idesc, 1u);
+            umma_tf32(tmem_base + (uint32_t)N, a2h, bl, idesc, 1u);
+          }
         }
         umma_commit(bar_empty + 8 * s);
         if (it == n_chunks - 1) umma_commit(bar_done);
@@ -251,7 +265,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
       mbar_wait(bar_done, 0);
       tc_fence_after();
     }
-    for (int d = 0; d < 2; ++d) {
+    for (int d = 0; d < (kStacked ? 1 : 2); ++d) {     // stacked: the one accumulator holds [out1 ; out2] = 128 rows
       for (int cc = 0; cc < N / 32; ++cc) {
         uint32_t v[32];
         if (n_chunks > 0) {
@@ -277,24 +291,43 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
   }
 }
 
-// fixed-order reduction of the per-CTA partials (and of the [grid][32][N] column-sum slabs)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ colsum_part,
-                                    int grid, int n, float* __restrict__ out1, int64_t ldo1,
-                                    float* __restrict__ out2, int64_t ldo2, float* __restrict__ colsum) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = 2 * kFeat * n;
+// Fixed-order reduction of the per-CTA partials (and of the [grid][32][N] column-sum slabs).  One
+// warp per group of 32 consecutive outputs: lane l owns output 32*g + l; the `grid` partials are cut into
+// kRedSeg contiguous segments summed by kRedSeg warps of the block concurrently (coalesced 128-byte
+// reads, independent loads in flight) and the segment sums are combined in segment order, so the
+// summation tree depends on `grid` only -- deterministic run to run.
+constexpr int kRedSeg = 8;
+__global__ void __launch_bounds__(32 * kRedSeg) wgrad_reduce_kernel(const float* __restrict__ partials,
+                                                                     const float* __restrict__ colsum_part, int grid, int n,
+                                                                     int feat, float* __restrict__ out1, int64_t ldo1,
+                                                                     float* __restrict__ out2, int64_t ldo2,
+                                                                     float* __restrict__ colsum) {
+  __shared__ float seg_sum[kRedSeg][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;          // output index
+  const int per = 2 * feat * n;                  // a CTA's partial: [2][feat][n] (stacked: 2*64 rows = one accumulator)
+  const int stride = 2 * kFeat * n;              // slab pitch of the workspace
+  const int c0 = (int)((int64_t)grid * seg / kRedSeg), c1 = (int)((int64_t)grid * (seg + 1) / kRedSeg);
+  float s = 0.f;
   if (i < per) {
-    float s = 0.f;
-    for (int c = 0; c < grid; ++c) s += partials[(int64_t)c * per + i];
-    const int d = i / (kFeat * n), r = (i / n) % kFeat, col = i % n;
-    if (d == 0) out1[(int64_t)r * ldo1 + col] = s;
-    else out2[(int64_t)r * ldo2 + col] = s;
+    for (int c = c0; c < c1; ++c) s += partials[(int64_t)c * stride + i];
   } else if (i < per + n && colsum != nullptr) {
     const int col = i - per;
-    float s = 0.f;
-    for (int c = 0; c < grid; ++c)
+    for (int c = c0; c < c1; ++c)
       for (int r = 0; r < kRowsPerChunk; ++r) s += colsum_part[((int64_t)c * kRowsPerChunk + r) * n + col];
-    colsum[col] = s;
+  }
+  seg_sum[seg][lane] = s;
+  __syncthreads();
+  if (seg != 0) return;
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < kRedSeg; ++k) tot += seg_sum[k][lane];
+  if (i < per) {
+    const int d = i / (feat * n), r = (i / n) % feat, col = i % n;
+    if (d == 0) out1[(int64_t)r * ldo1 + col] = tot;
+    else out2[(int64_t)r * ldo2 + col] = tot;
+  } else if (i < per + n && colsum != nullptr) {
+    colsum[i - per] = tot;
   }
 }
 
@@ -302,7 +335,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const fl
 
 int wgrad_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags) {
   if (!(flags & MPGNN_F_TF32X3)) return 0;
-  return m >= 1 && k1 == tcw::kFeat && k2 == tcw::kFeat && (n == 64 || n == 128);
+  return m >= 1 && k1 == k2 && (k1 == tcw::kFeat || k1 == tcw::kFeat / 2) && (n == 64 || n == 128);
 }
 
 static void wgrad_split(int64_t m, int* grid, int64_t* rows_per_cta) {
@@ -345,11 +378,21 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
     return MPGNN_OK;
   };
   const bool masked = a.b_actmask != nullptr;
-  if (a.n == 128) MPGNN_PROPAGATE(masked ? launch(tcw::wgrad_tc_kernel<128, true>) : launch(tcw::wgrad_tc_kernel<128, false>));
-  else MPGNN_PROPAGATE(masked ? launch(tcw::wgrad_tc_kernel<64, true>) : launch(tcw::wgrad_tc_kernel<64, false>));
-  const int total = 2 * tcw::kFeat * (int)a.n + (int)a.n;
-  tcw::wgrad_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(p.partials, p.colsum_part, grid, (int)a.n,
-                                                                          a.out1, a.ldo1, a.out2, a.ldo2, a.out_ones);
+  const bool stacked = a.k1 == tcw::kFeat / 2;
+  switch ((a.n == 128 ? 4 : 0) + (masked ? 2 : 0) + (stacked ? 1 : 0)) {
+    case 0: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, false, false>)); break;
+    case 1: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, false, true>)); break;
+    case 2: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, true, false>)); break;
+    case 3: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, true, true>)); break;
+    case 4: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, false>)); break;
+    case 5: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, true>)); break;
+    case 6: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, false>)); break;
+    default: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, true>)); break;
+  }
+  const int feat = (int)a.k1;
+  const int total = 2 * feat * (int)a.n + (int)a.n;
+  tcw::wgrad_reduce_kernel<<<(unsigned)ceil_div(total, 32), 32 * tcw::kRedSeg, 0, s>>>(
+      p.partials, p.colsum_part, grid, (int)a.n, feat, a.out1, a.ldo1, a.out2, a.ldo2, a.out_ones);
   MPGNN_LAUNCH_CHECK();
   return MPGNN_OK;
 }

@@ -116,7 +116,7 @@ class CandidateTrainer:
     the 999 x (mpgnn_train, mpgnn_validation) loop of main.py:1117-1134 as CUDA-graph replays."""
 
     def __init__(self, data_mpgnn, input_dim, hidden_dim, ll_output_dim, metapath, device=None, dropout_p=0.6,
-                 seed=None, precision="fp32", max_epochs=EPOCHS_PER_CANDIDATE):
+                 seed=None, precision="tf32x3", max_epochs=EPOCHS_PER_CANDIDATE):
         lib = _lib.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.st = _staged(data_mpgnn, self.device)
@@ -224,6 +224,54 @@ def mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_d
     _, _, f1_val = _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
                                     metapaths, epochs)
     return f1_val
+
+
+def mpgnn_parallel_multiple_batch(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, candidates,
+                                  epochs=EPOCHS_PER_CANDIDATE, seed=None, max_concurrent=8):
+    """The candidate fan-out of main.py:1444-1462 for ONE rank's block: `mpgnn_parallel_multiple` once per
+    candidate metapath, returning the list of validation macro-F1.  The candidates are independent
+    trainings of small models, so up to `max_concurrent` of them run at the same time on this GPU (one
+    device-resident trainer, CUDA graph and stream each); on graphs too small to fill the SMs that is
+    what turns the per-candidate latency into candidates/s.  Numbers are identical to the one-by-one
+    calls: the parameters are drawn sequentially on the host (`seed`, when given, is re-applied before
+    every candidate like the reference-side seam torch.manual_seed(30)) and each training is
+    deterministic on its own stream."""
+    import concurrent.futures
+    cands = [[int(r) for r in c] for c in candidates]
+    if not cands:
+        return []
+    if not all(1 <= len(c) <= 8 for c in cands):
+        out = []
+        for c in cands:
+            if seed is not None:
+                torch.manual_seed(seed)
+            out.append(mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, [c],
+                                               epochs=epochs))
+        return out
+    n = int(data_mpgnn.x.size(0))
+    # activations kept per trainer: (h, y) per hop + head buffers + gradients, ~ (4 L + 8) N H floats
+    est = 4 * n * int(hidden_dim) * (4 * max(len(c) for c in cands) + 8)
+    free = torch.cuda.mem_get_info()[0]
+    width = int(max(1, min(max_concurrent, len(cands), (free // 2) // max(est, 1))))
+    results = [None] * len(cands)
+    for lo in range(0, len(cands), width):
+        wave = []
+        for i in range(lo, min(lo + width, len(cands))):          # host-side draws stay sequential
+            if seed is not None:
+                torch.manual_seed(seed)
+            model = MPNetm(input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, 1, [cands[i]], device="cpu")
+            tr = CandidateTrainer(data_mpgnn, input_dim, hidden_dim, ll_output_dim, cands[i], dropout_p=model.dropout.p,
+                                  max_epochs=epochs)
+            tr.load_state_dict(model.state_dict())
+            wave.append((i, tr))
+        torch.cuda.synchronize()
+        with concurrent.futures.ThreadPoolExecutor(max_workers=len(wave)) as pool:
+            futs = [pool.submit(tr.run, epochs) for _, tr in wave]
+            for f in futs:
+                f.result()
+        for i, tr in wave:
+            results[i] = tr.last_val_f1
+    return results
 
 
 def mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,

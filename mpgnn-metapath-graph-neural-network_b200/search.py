@@ -491,7 +491,7 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     `eval_fn(meta)` -> validation macro-F1, `union_fn(metas)` -> test macro-F1 default to the device
     implementations; tests inject CPU stand-ins to exercise the fan-out and the rules.
     `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381)."""
-    from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_x
+    from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_x, mpgnn_parallel_multiple_batch
     comm = comm or Comm()
     if score_fn is None:
         def score_fn(d, rel):
@@ -500,10 +500,15 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     if bag_score_fn is None:
         def bag_score_fn(bag_data, rel, mlen):
             return score_relation_bags_parallel(bag_data, rel, input_dim, dataset, metapath_len=mlen)
+    batch_eval = None
     if eval_fn is None:
         def eval_fn(meta):
             torch.manual_seed(CANDIDATE_SEED)
             return mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, [meta])
+
+        def batch_eval(metas):          # the rank's whole block at once: independent trainers run concurrently
+            return mpgnn_parallel_multiple_batch(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
+                                                 metas, seed=CANDIDATE_SEED)
     if union_fn is None:
         def union_fn(metas):
             torch.manual_seed(CANDIDATE_SEED)
@@ -584,6 +589,13 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     lo, hi = candidate_block(len(final_metapaths_list), comm.size, comm.rank)
     done = {}
     mine = []
+    if batch_eval is not None:
+        uniq = []
+        for i in range(lo, hi):
+            if final_metapaths_list[i] not in uniq:
+                uniq.append(final_metapaths_list[i])
+        for meta, f1 in zip(uniq, batch_eval(uniq)):
+            done[str(meta)] = float(f1)
     for i in range(lo, hi):
         key = str(final_metapaths_list[i])
         if key not in done:                       # duplicates (main.py:1388) train to the same number under the seam

@@ -12,6 +12,6 @@ from .graph import RelationGraph, graph_for, clear_cache  # noqa: E402,F401
 from .mp_rgcn_layer import CustomRGCNConv, masked_edge_index  # noqa: E402,F401
 from .model import MPNetm  # noqa: E402,F401
 from .main import (Data, mpgnn_train, mpgnn_validation, mpgnn_test, mpgnn_parallel_multiple,  # noqa: E402,F401
-                   mpgnn_parallel_multiple_x, device_macro_f1, CandidateTrainer)
+                   mpgnn_parallel_multiple_x, mpgnn_parallel_multiple_batch, device_macro_f1, CandidateTrainer)
 from .search import (score_relation_parallel, node_types_and_connected_relations, create_edge_dictionary,  # noqa: E402,F401
                      greedy_search, Comm, run_scorer)
