@@ -43,6 +43,16 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the same command
+# (profiles/r01_tc6_ncu.md); None where no capture exists.
+NCU_TRAFFIC = {
+    "proj_fwd_tcgen05": 10.240e9 + 5.249e9,       # profiles/r01_tc6_ncu.md
+    "dgrad_nt_tcgen05": 5.321e9 + 10.191e9,       # profiles/r01_tc6_ncu.md
+    "wgrad_tn_tcgen05": 15.527e9 + 0.013e9,       # profiles/r01_tc5_ncu.md
+    "spmm_mean_fwd": 6.77e9,                      # profiles/r01_simt_ncu.md
+}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -107,6 +117,11 @@ def algorithmic_bytes(n, e_r, f):
         "layer_fwd_fused": 4 * (n * (f + f) + e_r * (f + 1) + (n + 1)),
         "layer_bwd": 4 * (n * (2 * f + 2 * f) + e_r * (2 * f + 2) + 2 * (n + 1)),
         "spmm_transpose_bwd": 4 * (e_r * (f + 1) + 2 * n * f + (n + 1)),
+        # dense kernels of the hop as built here (h, t and the [y>0] bitmask are materialised; g_z is not):
+        "proj_fwd": 4 * n * (2 * f + f) + n * f // 8,          # read h, x; write y (+ bitmask)
+        "wgrad_tn": 4 * n * 3 * f + n * f // 8,                # read h, x, g_y (+ bitmask)
+        "dgrad_nt": 4 * n * (f + 2 * f) + n * f // 8,          # read g_y (+ bitmask); write t = [g_z W^T/deg | g_z root^T]
+        "relu_dropout_bwd": 4 * n * 3 * f,
     }
 
 
@@ -284,22 +299,37 @@ def run_ours(args):
         per_kernel[k] = {"ms_per_launch": kms / max(calls, 1), "share": kms / total_ms, "calls": calls}
     dominant = max(kern, key=lambda k: kern[k][0]) if kern else None
     flops_proj = 2.0 * n * (2 * f) * f
+    # Every kernel of the hop streams its operands once: the binding roofline is HBM.  For the
+    # tensor-core contractions the 3xTF32 view is reported next to it (executed tf32 flops = 3 x algorithmic).
+    def _bytes_of(kname):
+        for key in ("spmm_mean_fwd", "spmm_transpose_bwd", "relu_dropout_bwd"):
+            if kname == key:
+                return ab[key]
+        for key in ("proj_fwd", "wgrad_tn", "dgrad_nt"):
+            if kname.startswith(key):
+                return ab[key]
+        return None
+    for k, v in per_kernel.items():
+        byts = _bytes_of(k)
+        if byts is not None:
+            v["algorithmic_bytes"] = byts
+            v["hbm_gbs"] = byts / (v["ms_per_launch"] * 1e-3) / 1e9
+            v["hbm_frac"] = v["hbm_gbs"] / hbm
+        if k.startswith(("proj_fwd", "wgrad_tn", "dgrad_nt")):
+            v["algorithmic_tflops"] = flops_proj / (v["ms_per_launch"] * 1e-3) / 1e12
+            v["executed_tf32_tflops"] = 3 * v["algorithmic_tflops"] if "tcgen05" in k else None
     roofline = None
-    if dominant is not None:
-        d_ms = per_kernel[dominant]["ms_per_launch"]
-        if dominant.startswith("spmm"):
-            byts = ab[dominant]
-            roofline = {"kernel": dominant, "bound": "hbm", "achieved": byts / (d_ms * 1e-3) / 1e9, "peak": hbm,
-                        "unit": "GB/s", "traffic": None, "algorithmic_bytes": byts}
-        elif dominant == "relu_dropout_bwd":
-            byts = 3 * 4 * n * f
-            roofline = {"kernel": dominant, "bound": "hbm", "achieved": byts / (d_ms * 1e-3) / 1e9, "peak": hbm,
-                        "unit": "GB/s", "traffic": None, "algorithmic_bytes": byts}
-        else:  # dense contractions: [N,2F]x[2F,F] each
-            roofline = {"kernel": dominant, "bound": "tensor", "achieved": flops_proj / (d_ms * 1e-3) / 1e12,
-                        "peak": tf, "unit": "TFLOP/s", "traffic": None, "algorithmic_flops": flops_proj}
-        roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        roofline["peak_source"] = how
+    if dominant is not None and _bytes_of(dominant) is not None:
+        d = per_kernel[dominant]
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["hbm_gbs"], "peak": hbm, "unit": "GB/s",
+                    "frac": d["hbm_frac"], "traffic": NCU_TRAFFIC.get(dominant), "algorithmic_bytes": d["algorithmic_bytes"],
+                    "peak_source": how,
+                    "tensor_view": None if "algorithmic_tflops" not in d else {
+                        "algorithmic_tflops": d["algorithmic_tflops"], "executed_tf32_tflops": d["executed_tf32_tflops"],
+                        "bf16_peak_tflops": tf, "frac_of_bf16_peak": d["algorithmic_tflops"] / tf,
+                        "note": "fp32-parity product = 3 tf32 MMA passes; tf32 runs at half the bf16 rate, so the "
+                                "ceiling of this formulation is bf16_peak/6"}}
+    hop_bytes = ab["layer_fwd_fused"] + ab["layer_bwd"] + 8 * n * f       # SURVEY 8d hop formulas, t materialised
     # the north-star kernel is always reported next to the dominant one
     spmm_roof = None
     if "spmm_mean_fwd" in per_kernel:
@@ -320,7 +350,10 @@ def run_ours(args):
                    "parallelism": "replicated graph, hops sharded by relation over %d GPU(s)" % world},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
-        "extra": {"graph_build_s": build_s, "rows_per_s": n * args.steps * world / (ms * 1e-3),
+        "extra": {"hop_roofline": {"algorithmic_bytes": hop_bytes, "achieved_gbs": hop_bytes / (ms / args.steps * 1e-3) / 1e9,
+                                   "frac": hop_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm,
+                                   "note": "SURVEY 8(d): B_fwd (fused layer) + B_bwd + 8 N F for the materialised t"},
+                  "graph_build_s": build_s, "rows_per_s": n * args.steps * world / (ms * 1e-3),
                   "mean_edges_per_hop": e_r_mean, "kernels": per_kernel, "spmm_mean_fwd_roofline": spmm_roof,
                   "candidate_scoring": cand},
     }
