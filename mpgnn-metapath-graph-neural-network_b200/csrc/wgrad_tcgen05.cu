@@ -226,10 +226,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
     const uint32_t s0 = smem_u32(smem);
     int s = 0;
     uint32_t sph = 0;
+    if (elect_one())          // one thread issues for the whole kernel (no per-chunk elect / reconvergence)
     for (int it = 0; it < n_chunks; ++it) {
       mbar_wait(bar_full + 8 * s, sph);
       tc_fence_after();
-      if (elect_one()) {
+      {
         const uint32_t st = s0 + (uint32_t)(s * stage_bytes);
 #pragma unroll
         for (int kg = 0; kg < kRowsPerChunk / 8; ++kg) {
@@ -253,9 +254,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
         umma_commit(bar_empty + 8 * s);
         if (it == n_chunks - 1) umma_commit(bar_done);
       }
-      __syncwarp();
       if (++s == kStagesW) { s = 0; sph ^= 1u; }
     }
+    __syncwarp();             // the idle lanes wait here, not at the teardown barrier
   } else {
     // ================================ final epilogue: TMEM -> per-CTA partial =============
     const int ew = warp - kProducerWarpsW;          // == warp % 4: TMEM lane quarter
