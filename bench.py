@@ -357,7 +357,7 @@ def run_ours(args):
                   "mean_edges_per_hop": e_r_mean, "kernels": per_kernel, "spmm_mean_fwd_roofline": spmm_roof,
                   "candidate_scoring": cand},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def candidate_scoring(rank, world, dev, dist, per_rank=8):
@@ -473,10 +473,29 @@ def run_reference(args):
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout (see main: library chatter goes to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    # NCCL / torchrun / nvcc banners must not share stdout with the JSON line: keep the real stdout aside and
+    # point fd 1 at stderr for everything else (child processes and C libraries included).
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
