@@ -12,6 +12,12 @@
 // STACKED along the MMA M dimension into one 128-wide tile ([h | x] per node row), so one accumulator
 // and three MMAs per K-step produce both gradients (rows 0-63 = A1^T B, rows 64-127 = A2^T B).
 //
+// Wide outputs (N = 128, A1/A2 128 wide): the roles are SWAPPED -- g_z^T (128 features) is the M operand and
+// [h | x] one 256-wide N operand, D^T[128 x 256] = g_z^T [h | x].  Three M128xN256xK8 MMAs per K-step instead of six
+// M128xN128xK8: the same tensor work with 36 KB instead of 48 KB of shared-memory operand reads per K-step, which is
+// what bounds this kernel (SS-mode operands).  The epilogue writes the transposed accumulator into the same
+// [2][128][N] partial layout.
+//
 // One persistent CTA per SM owns a contiguous range of rows (a fixed function of M, so the
 // summation tree is the same on every run and GPU count) and keeps BOTH 128xN accumulators in
 // TMEM for its whole range; at the end it writes one partial per CTA and a second kernel adds
@@ -79,6 +85,7 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t sbo) {
 // one 128-wide operand tile / one accumulator
 template <int N, bool kMasked, bool kStacked>
 __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p) {
+  constexpr bool kSwap = (N == 128) && !kStacked;      // g_z^T as the M operand, [h | x] as one N = 256 operand
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b_tile_bytes = kRowsPerChunk * N * 4;                    // one of hi / lo
   const int stage_bytes = 4 * kATileBytes + 2 * b_tile_bytes;        // a1 hi/lo, a2 hi/lo, b hi/lo
@@ -90,10 +97,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStagesW);
   const uint32_t bar_done = smem_u32(bars + 2 * kStagesW);
 
-  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
-  int64_t r_end = r_begin + p.rows_per_cta;
-  if (r_end > p.m) r_end = p.m;
-  const int n_chunks = r_begin < r_end ? (int)((r_end - r_begin + kRowsPerChunk - 1) / kRowsPerChunk) : 0;
+  // chunk c of this CTA covers rows (c * gridDim.x + blockIdx.x) * 32 ..: at any moment the CTAs of the grid read
+  // one contiguous window of each operand (DRAM page locality; per-CTA contiguous ranges gave 444 scattered
+  // streams and 4.0 TB/s).  The assignment is a function of the shape only, so the summation order is fixed.
+  const int64_t total_chunks = (p.m + kRowsPerChunk - 1) / kRowsPerChunk;
+  const int n_chunks = (int)(total_chunks > blockIdx.x ? (total_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  const int64_t r_end = p.m;
 
   if (tid == 0) {
     for (int s = 0; s < kStagesW; ++s) {
@@ -127,8 +136,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
     for (int u = 0; u < 2; ++u) {
       a_row[u] = warp * 2 + u;
       a_col[u] = lane * 4;
-      a_soff[u] = (int)mn_tile_offset16(lane, a_row[u], kFeat / 32);
+      a_soff[u] = (int)mn_tile_offset16(lane, a_row[u], kSwap ? 2 * kFeat / 32 : kFeat / 32);
     }
+    // swapped roles: one [h | x] tile of 8 MN atoms (hi @0, lo @32K); x goes to atoms 4-7 = 16-byte units 32..63
+    int a2_soff[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) a2_soff[u] = kSwap ? (int)mn_tile_offset16(lane + 32, a_row[u], 2 * kFeat / 32) : a_soff[u];
     int b_row[2], b_col[2], b_soff[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -149,7 +162,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
     constexpr int b_words = N / 32;
     int pf = 0;                                            // next chunk to prefetch
     auto issue = [&](float4 (&dst)[6], uint32_t (&mw)[2]) {
-      const int64_t row0 = r_begin + (int64_t)pf * kRowsPerChunk;
+      const int64_t row0 = ((int64_t)pf * gridDim.x + blockIdx.x) * kRowsPerChunk;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -179,8 +192,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
       uint8_t* st = smem + (size_t)s * stage_bytes;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        split_store(st + a_soff[u], kATileBytes, src[u]);                         // a1: hi @0, lo @16K
-        if (!kStacked) split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
+        if (kSwap) {
+          split_store(st + a_soff[u], 2 * kATileBytes, src[u]);                    // [h | x] tile: hi @0, lo @32K
+          split_store(st + a2_soff[u], 2 * kATileBytes, src[2 + u]);
+        } else {
+          split_store(st + a_soff[u], kATileBytes, src[u]);                        // a1: hi @0, lo @16K
+          if (!kStacked) split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
+        }
         if (u < n_units_b) {
           float4 b = src[4 + u];
           if (masked) {                                   // fused ReLU/dropout backward: g_z = g_y gated by [y > 0]
@@ -205,11 +223,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
         const int it = it0 + j;
         if (it < n_chunks) {
           mbar_wait(bar_empty + 8 * s, sph ^ 1u);
+#ifndef MPGNN_WGRAD_EXP_NOFILL
           store(s, buf[j], mbuf[j]);
+#endif
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full + 8 * s);
+#ifndef MPGNN_WGRAD_EXP_NOFILL
           if (it + 2 < n_chunks) issue(buf[j], mbuf[j]);
+#endif
           if (++s == kStagesW) { s = 0; sph ^= 1u; }
         }
       }
@@ -234,7 +256,22 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
         const uint32_t st = s0 + (uint32_t)(s * stage_bytes);
 #pragma unroll
         for (int kg = 0; kg < kRowsPerChunk / 8; ++kg) {
+#ifdef MPGNN_WGRAD_EXP_NOMMA
+          if (kg > 0 || it > 0) continue;
+#endif
           // one MMA consumes K = 8 node rows = two groups of 4 K-rows
+          if (kSwap) {
+            const uint32_t hx_sbo = (2 * kFeat / 32) * 512;
+            const uint32_t go = kg * 2 * b_sbo, ho = kg * 2 * hx_sbo;
+            const uint64_t gh = desc_mn(st + 4 * kATileBytes + go, b_sbo), gl = desc_mn(st + 4 * kATileBytes + b_tile_bytes + go, b_sbo);
+            const uint64_t hh = desc_mn(st + ho, hx_sbo), hl = desc_mn(st + 2 * kATileBytes + ho, hx_sbo);
+            const uint32_t idesc_t = make_idesc_mn(N, 2 * kFeat);
+            const uint32_t acc_t = (it | kg) != 0 ? 1u : 0u;
+            umma_tf32(tmem_base, gh, hh, idesc_t, acc_t);
+            umma_tf32(tmem_base, gl, hh, idesc_t, 1u);
+            umma_tf32(tmem_base, gh, hl, idesc_t, 1u);
+            continue;
+          }
           const uint32_t ao = kg * 2 * a_sbo, bo = kg * 2 * b_sbo;
           const uint64_t a1h = desc_mn(st + ao, a_sbo), a1l = desc_mn(st + kATileBytes + ao, a_sbo);
           const uint64_t a2h = desc_mn(st + 2 * kATileBytes + ao, a_sbo);
@@ -266,6 +303,19 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
       mbar_wait(bar_done, 0);
       tc_fence_after();
     }
+    if (kSwap) {      // D^T: lane = output column n, TMEM column j = row of [g_W ; g_root]
+      for (int cc = 0; cc < 2 * kFeat / 32; ++cc) {
+        uint32_t v[32];
+        if (n_chunks > 0) {
+          tmem_ld32(tmem_base + (uint32_t)(cc * 32) + ((uint32_t)(ew * 32) << 16), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) part[(int64_t)(cc * 32 + q) * N + mrow] = __uint_as_float(v[q]);
+      }
+    } else
     for (int d = 0; d < (kStacked ? 1 : 2); ++d) {     // stacked: the one accumulator holds [out1 ; out2] = 128 rows
       for (int cc = 0; cc < N / 32; ++cc) {
         uint32_t v[32];
