@@ -319,3 +319,69 @@ def test_hop_linearity_at_scale():
     assert bool((ei[0][eid.long()] == rows).all())
     same_row = rows[1:] == rows[:-1]
     assert bool((eid[1:][same_row] > eid[:-1][same_row]).all())  # stable inside each bucket
+
+
+def _dot64(a, b, block=1 << 20):
+    """<a, b> accumulated in float64 block by block (the operands are 5 GB each)."""
+    tot = 0.0
+    a2, b2 = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
+    for i in range(0, a2.size(0), block):
+        tot += float((a2[i:i + block].double() * b2[i:i + block].double()).sum())
+    return tot
+
+
+@pytest.mark.timeout(600, method="thread")
+def test_c4_full_size_properties():
+    """BASELINE.json configs[3] at FULL size (10M nodes / 200M edges / 64 relations / hidden 128), through the
+    properties the domain offers instead of the oracle:
+      * K1: every edge lands in exactly one bucket (counts = bincount of the types; ptr monotone; eids of a sampled
+        relation are a stable selection of its edges);
+      * forward (K2 + K3, tensor-core path): linear in x for fixed weights;
+      * backward (K4, dgrad, transposed K2): the adjoint identities of the bilinear map y = mean_r(x) W + x root + b:
+        <y(x), g> = <x, g_x>  and  <y, g> = <W, g_W> + <root, g_root> + <b, g_b>."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 * 2 ** 30:
+        pytest.skip("needs ~60 GB of free HBM")
+    n, e, r, f = 10_000_000, 200_000_000, 64, 128
+    g = torch.Generator(device=DEV).manual_seed(0)
+    ei = torch.randint(0, n, (2, e), device=DEV, generator=g)
+    et = torch.randint(0, r, (e,), device=DEV, generator=g)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, r)
+    counts = torch.bincount(et, minlength=r).cpu().numpy()
+    assert np.array_equal(np.asarray(graph.relation_counts), counts) and int(counts.sum()) == e
+    rel = 37
+    p, idx, eid = graph.relation_view(rel)
+    assert bool((p[1:] >= p[:-1]).all()) and int(p[-1]) == int(counts[rel])
+    assert bool((et[eid.long()] == rel).all()) and bool((ei[1][eid.long()] == idx.long()).all())
+    rows = torch.repeat_interleave(torch.arange(n, device=DEV), (p[1:] - p[:-1]).long())
+    assert bool((ei[0][eid.long()] == rows).all())
+    same_row = rows[1:] == rows[:-1]
+    assert bool((eid[1:][same_row] > eid[:-1][same_row]).all())            # stable inside each bucket
+    del ei, et, rows, same_row
+    conv = mpgnn_b200.CustomRGCNConv(f, f, 1, flow="target_to_source", device=DEV)
+    with torch.no_grad():
+        conv.bias.copy_(torch.randn(f, device=DEV, generator=g) * 0.1)
+    x1 = torch.randn(n, f, device=DEV, generator=g)
+    x2 = torch.randn(n, f, device=DEV, generator=g)
+    with torch.no_grad():
+        zero = conv.hop(rel, torch.zeros(1, f, device=DEV).expand(n, f), graph, precision="tf32x3")   # = bias rows
+        y1 = conv.hop(rel, x1, graph, precision="tf32x3")
+        y2 = conv.hop(rel, x2, graph, precision="tf32x3")
+        x2.mul_(-2.0).add_(x1, alpha=0.5)                                  # x2 <- 0.5 x1 - 2 x2
+        y12 = conv.hop(rel, x2, graph, precision="tf32x3")
+        y2.mul_(-2.0).add_(y1, alpha=0.5).add_(zero, alpha=2.5)            # affine: bias counted once
+        assert rel_err(y12, y2) < FP32_TOL
+    del y2, y12, x2, zero
+    # adjoint identities through autograd (the C-ABI backward)
+    x1.requires_grad_(True)
+    y = conv.hop(rel, x1, graph, precision="tf32x3")
+    gy = torch.randn(n, f, device=DEV, generator=g)
+    y.backward(gy)
+    lin = _dot64(y.detach(), gy) - _dot64(conv.bias.detach().expand(n, f), gy)     # the part linear in x
+    via_x = _dot64(x1.detach(), x1.grad)
+    via_w = (_dot64(conv.weight.detach(), conv.weight.grad) + _dot64(conv.root.detach(), conv.root.grad))
+    scale = (_dot64(y.detach(), y.detach()) * _dot64(gy, gy)) ** 0.5             # Cauchy-Schwarz scale of <y, g>
+    assert abs(lin - via_x) < 1e-5 * scale, (lin, via_x, scale)
+    assert abs(lin - via_w) < 1e-5 * scale, (lin, via_w, scale)
+    gb = conv.bias.grad.double()
+    assert float((gb - gy.double().sum(0)).abs().max()) < 1e-5 * float(gy.double().abs().sum(0).max())
