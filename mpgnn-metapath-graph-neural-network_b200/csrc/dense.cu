@@ -11,6 +11,44 @@ namespace mpgnn {
 // ----------------------------------------------------------------------------------------
 // gemm_rows: out[M,N] = epi([A1|A2] @ B), B row-major [K,N]
 // ----------------------------------------------------------------------------------------
+// Epilogue of one row x 4 consecutive columns (col0 % 4 == 0): bias, 1/deg on the first deg_cols columns, relu,
+// ReLU-backward gate, dropout (seeded counter stream or explicit mask bits); shared by every gemm_rows kernel.
+__device__ __forceinline__ uint64_t gr_launch_key(const GemmRowsArgs& a) {
+  if (a.dropout_mode != 1) return 0ull;
+  return dropout_launch_key(a.seed, a.offset + (a.offset_ptr != nullptr ? *a.offset_ptr : 0ull));
+}
+__device__ __forceinline__ void gr_epilogue(const GemmRowsArgs& a, uint64_t launch_key, int64_t row, int64_t col0,
+                                            const float (&acc)[4]) {
+  const float scale = a.dropout_mode ? a.dropout_scale : 1.f;
+  const int64_t mask_ld = (a.n + 7) / 8;
+  float inv_deg_den = 1.f;
+  if (a.deg_ptr != nullptr) {
+    const int d = __ldg(a.deg_ptr + row + 1) - __ldg(a.deg_ptr + row);
+    inv_deg_den = (float)max(d, 1);
+  }
+  // the 4 columns are one aligned block of the dropout stream: one block word per row
+  uint2 dw = make_uint2(0u, 0u);
+  if (a.dropout_mode == 1) dw = dropout_block(dropout_row_key(launch_key, (uint64_t)row), (uint32_t)(col0 >> 2));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t col = col0 + j;
+    if (col >= a.n) continue;
+    float v = acc[j];
+    if (a.bias != nullptr) v += __ldg(a.bias + col);
+    if (col < a.deg_cols) v = v / inv_deg_den;
+    if (a.relu) v = fmaxf(v, 0.f);
+    if (a.gate != nullptr) v = (__ldg(a.gate + row * a.ldgate + col) > 0.f) ? v : 0.f;
+    if (a.dropout_mode == 1) {
+      const uint32_t half = (j & 2) ? dw.y : dw.x;
+      v = ((half >> (16 * (j & 1))) & 0xFFFFu) >= a.dropout_thr16 ? v * scale : 0.f;
+    } else if (a.dropout_mode == 2) {
+      const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
+      v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;
+    }
+    a.out[row * a.ldo + col] = v;
+  }
+}
+
 constexpr int GR_BM = 128, GR_BN = 64, GR_BK = 16, GR_THREADS = 256, GR_PAD = 4;
 
 __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
@@ -64,47 +102,83 @@ __global__ void __launch_bounds__(GR_THREADS) gemm_rows_kernel(GemmRowsArgs a) {
     __syncthreads();
   }
 
-  const float scale = a.dropout_mode ? a.dropout_scale : 1.f;
-  const uint64_t drop_off = a.offset + (a.offset_ptr != nullptr ? *a.offset_ptr : 0ull);
-  const uint64_t launch_key = a.dropout_mode == 1 ? dropout_launch_key(a.seed, drop_off) : 0ull;
-  const int64_t mask_ld = (a.n + 7) / 8;
+  const uint64_t launch_key = gr_launch_key(a);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t row = row0 + ty * 8 + i;
     if (row >= a.m) continue;
-    float inv_deg_den = 1.f;
-    if (a.deg_ptr != nullptr) {
-      const int d = __ldg(a.deg_ptr + row + 1) - __ldg(a.deg_ptr + row);
-      inv_deg_den = (float)max(d, 1);
-    }
-    // the thread's 4 columns are one aligned block of the dropout stream: one block word per row
-    uint2 dw = make_uint2(0u, 0u);
-    if (a.dropout_mode == 1) dw = dropout_block(dropout_row_key(launch_key, (uint64_t)row), (uint32_t)((col0 + tx * 4) >> 2));
+    gr_epilogue(a, launch_key, row, col0 + tx * 4, acc[i]);
+  }
+}
+
+// Thin shapes of the candidate models (2-d one-hot input layer, 2-class head): K <= 8 or N <= 8.  The tiled kernel
+// above spends its time on tile bookkeeping there; these stream the wide operand once.
+// (a) K <= 8: one thread = one row x 4 columns, the <= 8 A values of the row are broadcast loads.
+__global__ void __launch_bounds__(256) gemm_rows_smallk_kernel(GemmRowsArgs a) {
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int64_t row = (int64_t)blockIdx.x * 16 + ty;
+  const int64_t col0 = (int64_t)blockIdx.y * 64 + tx * 4;
+  if (row >= a.m || col0 >= a.n) return;
+  const int ktot = (int)(a.k1 + a.k2);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < ktot; ++k) {
+    const float av = k < a.k1 ? __ldg(a.a1 + row * a.lda1 + k) : __ldg(a.a2 + row * a.lda2 + (k - a.k1));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t col = col0 + tx * 4 + j;
-      if (col >= a.n) continue;
-      float v = acc[i][j];
-      if (a.bias != nullptr) v += __ldg(a.bias + col);
-      if (col < a.deg_cols) v = v / inv_deg_den;
-      if (a.relu) v = fmaxf(v, 0.f);
-      if (a.gate != nullptr) v = (__ldg(a.gate + row * a.ldgate + col) > 0.f) ? v : 0.f;
-      if (a.dropout_mode == 1) {
-        const uint32_t half = (j & 2) ? dw.y : dw.x;
-        v = ((half >> (16 * (j & 1))) & 0xFFFFu) >= a.dropout_thr16 ? v * scale : 0.f;
-      } else if (a.dropout_mode == 2) {
-        const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
-        v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;
-      }
-      a.out[row * a.ldo + col] = v;
+    for (int j = 0; j < 4; ++j)
+      if (col0 + j < a.n) acc[j] = fmaf(av, __ldg(a.b + (int64_t)k * a.n + col0 + j), acc[j]);
+  }
+  gr_epilogue(a, gr_launch_key(a), row, col0, acc);
+}
+
+// (b) N <= 4: 8 lanes per row split K in 16-byte pieces, B (K x N <= 2048 floats) staged in shared memory, the 8
+// partial dots are combined with a fixed xor tree, lane 0 of the group runs the epilogue.
+__global__ void __launch_bounds__(256) gemm_rows_smalln_kernel(GemmRowsArgs a) {
+  __shared__ float Bs[2048];
+  const int ktot = (int)(a.k1 + a.k2), n = (int)a.n;
+  for (int i = threadIdx.x; i < ktot * n; i += 256) Bs[i] = __ldg(a.b + i);
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int64_t row = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (row < a.m) {
+    for (int k4 = sub * 4; k4 < ktot; k4 += 32) {
+      const float4 v = k4 < a.k1 ? __ldg(reinterpret_cast<const float4*>(a.a1 + row * a.lda1 + k4))
+                                 : __ldg(reinterpret_cast<const float4*>(a.a2 + row * a.lda2 + (k4 - a.k1)));
+      const float av[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < n) acc[j] = fmaf(av[e], Bs[(k4 + e) * n + j], acc[j]);
     }
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+  }
+  if (row < a.m && sub == 0) gr_epilogue(a, gr_launch_key(a), row, 0, acc);
 }
 
 int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s) {
   if (a.m <= 0 || a.n <= 0) return MPGNN_OK;
   MPGNN_REQUIRE(a.k1 >= 0 && a.k2 >= 0 && (a.k1 == 0 || a.a1) && (a.k2 == 0 || a.a2) && a.b && a.out, MPGNN_EINVAL,
                 "gemm_rows: bad arguments");
+  const int64_t ktot = a.k1 + a.k2;
+  if (ktot >= 1 && ktot <= 8 && ceil_div(a.n, 64) <= 65535) {
+    dim3 grid((unsigned)ceil_div(a.m, 16), (unsigned)ceil_div(a.n, 64));
+    gemm_rows_smallk_kernel<<<grid, 256, 0, s>>>(a);
+    MPGNN_LAUNCH_CHECK();
+    return MPGNN_OK;
+  }
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.n <= 4 && ktot * a.n <= 2048 && a.k1 % 4 == 0 && a.k2 % 4 == 0 && (a.k1 == 0 || (al16(a.a1) && a.lda1 % 4 == 0)) &&
+      (a.k2 == 0 || (al16(a.a2) && a.lda2 % 4 == 0))) {
+    gemm_rows_smalln_kernel<<<(unsigned)ceil_div(a.m, 32), 256, 0, s>>>(a);
+    MPGNN_LAUNCH_CHECK();
+    return MPGNN_OK;
+  }
   const int64_t gx = ceil_div(a.m, GR_BM), gy = ceil_div(a.n, GR_BN);
   MPGNN_REQUIRE(gy <= 65535, MPGNN_ENOTSUP, "gemm_rows: N=%lld too wide", (long long)a.n);
   dim3 grid((unsigned)gx, (unsigned)gy);
@@ -123,7 +197,10 @@ static void tn_split(int64_t m, int64_t ktot, int64_t n, int64_t* splits, int64_
   const int64_t tiles = ceil_div(ktot, TN_BK) * ceil_div(n, TN_BN);
   int64_t target = (int64_t)kNumSMs * 8 / (tiles > 0 ? tiles : 1);
   if (target < 1) target = 1;
-  int64_t sp = ceil_div(m, 512);
+  // thin outputs (<= 8 rows or <= 4 columns) have one tile: give the streaming kernels more, shorter row ranges
+  const bool thin = ktot <= 8 || n <= 4;
+  int64_t sp = ceil_div(m, thin ? 128 : 512);
+  if (thin) target = 2048;
   if (sp > target) sp = target;
   if (sp < 1) sp = 1;
   int64_t rps = align_up(ceil_div(m, sp), TN_BR);
@@ -214,6 +291,70 @@ __global__ void gemm_tn_reduce_kernel(GemmTnArgs a, int64_t ktot, int64_t splits
   }
 }
 
+// Thin gemm_tn shapes, same [split][ktot][n] partial layout and the same fixed-order second pass as the tiled kernel.
+// (a) ktot <= 8 (input-layer gradients: [h | x | 1]^T g_z with 2-d features): thread = column, 4 row lanes per
+//     block; B is read once, coalesced; the A values of a row are broadcast loads.
+__global__ void __launch_bounds__(256) gemm_tn_smallk_kernel(GemmTnArgs a, int ktot, int64_t rows_per_split) {
+  __shared__ float red[4][8][64];
+  const int c = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int64_t col = (int64_t)blockIdx.x * 64 + c;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(a.m, r_begin + rows_per_split);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (col < a.n) {
+    for (int64_t row = r_begin + rl; row < r_end; row += 4) {
+      const float bv = __ldg(a.b + row * a.ldb + col);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k >= ktot) break;
+        float av;
+        if (k < a.k1) av = __ldg(a.a1 + row * a.lda1 + k);
+        else if (k < a.k1 + a.k2) av = __ldg(a.a2 + row * a.lda2 + (k - a.k1));
+        else av = 1.f;
+        acc[k] = fmaf(av, bv, acc[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][k][c] = acc[k];
+  __syncthreads();
+  if (rl == 0 && col < a.n) {
+    float* part = a.partials + (int64_t)blockIdx.y * ktot * a.n;
+    for (int k = 0; k < ktot; ++k) part[(int64_t)k * a.n + col] = ((red[0][k][c] + red[1][k][c]) + red[2][k][c]) + red[3][k][c];
+  }
+}
+
+// (b) n <= 4 (2-class head gradients: [a1 | 1]^T g_logits): thread = row of the output (k < ktot <= 128), 2 row
+//     lanes per block; A is read once, coalesced; the <= 4 B values of a row are broadcast loads.
+__global__ void __launch_bounds__(256) gemm_tn_smalln_kernel(GemmTnArgs a, int ktot, int64_t rows_per_split) {
+  __shared__ float red[2][4][128];
+  const int k = threadIdx.x & 127, rl = threadIdx.x >> 7;
+  const int n = (int)a.n;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r_end = min(a.m, r_begin + rows_per_split);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < ktot) {
+    for (int64_t row = r_begin + rl; row < r_end; row += 2) {
+      float av;
+      if (k < a.k1) av = __ldg(a.a1 + row * a.lda1 + k);
+      else if (k < a.k1 + a.k2) av = __ldg(a.a2 + row * a.lda2 + (k - a.k1));
+      else av = 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < n) acc[j] = fmaf(av, __ldg(a.b + row * a.ldb + j), acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[rl][j][k] = acc[j];
+  __syncthreads();
+  if (rl == 0 && k < ktot) {
+    float* part = a.partials + (int64_t)blockIdx.y * ktot * a.n;
+    for (int j = 0; j < n; ++j) part[(int64_t)k * a.n + j] = red[0][j][k] + red[1][j][k];
+  }
+}
+
 int launch_gemm_tn(const GemmTnArgs& a, cudaStream_t s) {
   const int64_t ktot = a.k1 + a.k2 + (a.ones_row ? 1 : 0);
   if (ktot <= 0 || a.n <= 0) return MPGNN_OK;
@@ -224,8 +365,16 @@ int launch_gemm_tn(const GemmTnArgs& a, cudaStream_t s) {
   MPGNN_REQUIRE(splits <= 65535, MPGNN_ENOTSUP, "gemm_tn: too many splits");
   const int tiles_n = (int)ceil_div(a.n, TN_BN);
   const int64_t tiles = ceil_div(ktot, TN_BK) * tiles_n;
-  dim3 grid((unsigned)tiles, (unsigned)splits);
-  gemm_tn_kernel<<<grid, TN_THREADS, 0, s>>>(a, ktot, rps, tiles_n);
+  if (ktot <= 8) {
+    dim3 grid((unsigned)ceil_div(a.n, 64), (unsigned)splits);
+    gemm_tn_smallk_kernel<<<grid, 256, 0, s>>>(a, (int)ktot, rps);
+  } else if (a.n <= 4 && ktot <= 128) {
+    dim3 grid(1, (unsigned)splits);
+    gemm_tn_smalln_kernel<<<grid, 256, 0, s>>>(a, (int)ktot, rps);
+  } else {
+    dim3 grid((unsigned)tiles, (unsigned)splits);
+    gemm_tn_kernel<<<grid, TN_THREADS, 0, s>>>(a, ktot, rps, tiles_n);
+  }
   MPGNN_LAUNCH_CHECK();
   const int64_t total = ktot * a.n;
   gemm_tn_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a, ktot, splits);

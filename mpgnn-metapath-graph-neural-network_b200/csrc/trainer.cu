@@ -21,6 +21,12 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
             const uint32_t* actmask, const float* gy, int64_t f_in, const float* w, const float* root, int64_t f_out,
             uint32_t flags, double p, float* gx, float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes,
             cudaStream_t s);
+int proj_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags);
+int64_t proj_tcgen05_workspace_floats(int64_t k, int64_t n);
+int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, cudaStream_t s);
+int wgrad_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags);
+int64_t wgrad_tcgen05_workspace_floats(int64_t m, int64_t n);
+int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s);
 int launch_logsoftmax_nll(const float* logits, int64_t n, int64_t c, const int64_t* idx, const int64_t* y,
                           int64_t n_idx, float* logp, float* loss, float* glogits, void* ws, int64_t ws_bytes,
                           cudaStream_t s);
@@ -209,7 +215,11 @@ static int trainer_forward(Trainer* t, bool train, cudaStream_t s) {
   GemmRowsArgs a{};
   a.a1 = in; a.lda1 = H; a.k1 = H; a.b = t->params + t->off_w1; a.m = n; a.n = H;
   a.bias = t->params + t->off_b1; a.relu = 1; a.out = t->a1; a.ldo = H;
-  MPGNN_PROPAGATE(launch_gemm_rows(a, s));                                   // a1 = relu(E W1t + b1)
+  // a1 = relu(E W1t + b1); the scratch at the head of t->ws is free between hops (everything is stream ordered)
+  const bool head_tc = (t->flags & MPGNN_F_TF32X3) && proj_tcgen05_supported(n, H, 0, H, t->flags) &&
+                       proj_tcgen05_workspace_floats(H, H) * 4 <= t->ws_bytes;
+  if (head_tc) MPGNN_PROPAGATE(launch_proj_tcgen05_ws(a, t->flags, static_cast<float*>(t->ws), s));
+  else MPGNN_PROPAGATE(launch_gemm_rows(a, s));
   GemmRowsArgs b{};
   b.a1 = t->a1; b.lda1 = H; b.k1 = H; b.b = t->params + t->off_w2; b.m = n; b.n = C;
   b.bias = t->params + t->off_b2; b.out = t->lg; b.ldo = C;
@@ -246,12 +256,22 @@ static int trainer_backward(Trainer* t, cudaStream_t s) {
   t1.a1 = e_last; t1.lda1 = H; t1.k1 = H; t1.ones_row = 1; t1.b = t->gz1; t1.ldb = H; t1.n = H; t1.m = n;
   t1.out1 = t->grads + t->off_w1; t1.ldo1 = H; t1.out_ones = t->grads + t->off_b1;
   t1.partials = partials; t1.partial_capacity_floats = pf;
-  MPGNN_PROPAGATE(launch_gemm_tn(t1, s));
+  if ((t->flags & MPGNN_F_TF32X3) && wgrad_tcgen05_supported(n, H, 0, H, t->flags) &&
+      wgrad_tcgen05_workspace_floats(n, H) * 4 <= t->ws_bytes) {
+    t1.ones_row = 0;
+    MPGNN_PROPAGATE(launch_wgrad_tcgen05(t1, static_cast<float*>(t->ws), s));      // also fills out_ones = colsum(g_z1)
+  } else {
+    MPGNN_PROPAGATE(launch_gemm_tn(t1, s));
+  }
   // g_E = g_z1 W1t^T
   MPGNN_PROPAGATE(launch_pack_b(t->packed, H, t->params + t->off_w1, 1, H, H, H, s));   // B(k=o, n=i) = W1t[i*H + o]
   GemmRowsArgs b{};
   b.a1 = t->gz1; b.lda1 = H; b.k1 = H; b.b = t->packed; b.m = n; b.n = H; b.out = t->gxa; b.ldo = H;
-  MPGNN_PROPAGATE(launch_gemm_rows(b, s));
+  if ((t->flags & MPGNN_F_TF32X3) && proj_tcgen05_supported(n, H, 0, H, t->flags) &&
+      proj_tcgen05_workspace_floats(H, H) * 4 <= t->ws_bytes)
+    MPGNN_PROPAGATE(launch_proj_tcgen05_ws(b, t->flags, static_cast<float*>(t->ws), s));
+  else
+    MPGNN_PROPAGATE(launch_gemm_rows(b, s));
   float* gy = t->gxa;
   float* gx = t->gxb;
   for (int k = t->n_layers - 1; k >= 0; --k) {

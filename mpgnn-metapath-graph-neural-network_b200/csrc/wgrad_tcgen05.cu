@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
         const bool ok = ra < r_end;
         if (kStacked) {      // [A1 row | A2 row]: lanes 0-15 fetch the 64 floats of A1, lanes 16-31 those of A2
           const float* src = lane < 16 ? p.a1 + ra * p.lda1 + a_col[u] : p.a2 + ra * p.lda2 + (a_col[u] - 64);
-          dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(src)) : z;
+          dst[u] = (ok && (lane < 16 || p.a2 != nullptr)) ? __ldg(reinterpret_cast<const float4*>(src)) : z;   // a2 may be absent
           dst[2 + u] = z;
         } else {
           dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a1 + ra * p.lda1 + a_col[u])) : z;
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(32 * kRedSeg) wgrad_reduce_kernel(const float*
   if (i < per) {
     const int d = i / (feat * n), r = (i / n) % feat, col = i % n;
     if (d == 0) out1[(int64_t)r * ldo1 + col] = tot;
-    else out2[(int64_t)r * ldo2 + col] = tot;
+    else if (out2 != nullptr) out2[(int64_t)r * ldo2 + col] = tot;
   } else if (i < per + n && colsum != nullptr) {
     colsum[i - per] = tot;
   }
@@ -392,7 +392,9 @@ int launch_wgrad_tma(const GemmTnArgs& a, int grid, float* partials, int64_t par
 
 int wgrad_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags) {
   if (!(flags & MPGNN_F_TF32X3)) return 0;
-  return m >= 1 && k1 == k2 && (k1 == tcw::kFeat || k1 == tcw::kFeat / 2) && (n == 64 || n == 128);
+  if (m < 1 || !(n == 64 || n == 128)) return 0;
+  if (k1 == tcw::kFeat / 2 && k2 == 0) return 1;          // one 64-wide operand (head layer): stacked tile, second half zero
+  return k1 == k2 && (k1 == tcw::kFeat || k1 == tcw::kFeat / 2);
 }
 
 static void wgrad_split(int64_t m, int* grid, int64_t* rows_per_cta) {
@@ -413,14 +415,15 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   MPGNN_REQUIRE(wgrad_tcgen05_supported(a.m, a.k1, a.k2, a.n, MPGNN_F_TF32X3), MPGNN_ENOTSUP,
                 "wgrad_tcgen05: unsupported shape");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  MPGNN_REQUIRE(al16(a.a1) && al16(a.a2) && al16(a.b) && a.lda1 % 4 == 0 && a.lda2 % 4 == 0 && a.ldb % 4 == 0,
+  MPGNN_REQUIRE(al16(a.a1) && al16(a.b) && a.lda1 % 4 == 0 && a.ldb % 4 == 0 &&
+                    (a.k2 == 0 || (al16(a.a2) && a.lda2 % 4 == 0)),
                 MPGNN_EINVAL, "wgrad_tcgen05: operands must be 16-byte aligned with strides multiple of 4");
   int grid;
   int64_t rpc;
   wgrad_split(a.m, &grid, &rpc);
   tcw::ParamsW p{};
   p.a1 = a.a1; p.lda1 = a.lda1;
-  p.a2 = a.a2; p.lda2 = a.lda2;
+  p.a2 = a.k2 > 0 ? a.a2 : nullptr; p.lda2 = a.lda2;
   p.b = a.b; p.ldb = a.ldb; p.n = (int)a.n;
   p.m = a.m; p.rows_per_cta = rpc;
   p.b_actmask = a.b_actmask; p.b_scale = a.b_scale;
