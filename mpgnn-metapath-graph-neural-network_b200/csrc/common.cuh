@@ -52,6 +52,7 @@ struct ScopedTimer {
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kMaxDynSmem = 232448;   // 227 KB: opt-in dynamic shared memory per CTA on sm_100
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

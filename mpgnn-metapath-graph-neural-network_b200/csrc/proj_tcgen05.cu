@@ -547,7 +547,11 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   else map2 = map1;
   MPGNN_PROPAGATE(make_tensor_map(&map_out, a.out, a.m, a.n, a.ldo, 32));
   auto launch = [&](auto kernel) -> int {
-    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the opt-in limit is per function and process wide: always raise it to the device maximum, so that concurrent
+    // launches of the same kernel with different tile sizes (candidate trainers on several host threads) cannot
+    // lower it under one another
+    MPGNN_REQUIRE(smem <= (size_t)kMaxDynSmem, MPGNN_ENOTSUP, "shared memory request %zu exceeds the device limit", smem);
+    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p, map1, map2, map_out);
     MPGNN_LAUNCH_CHECK();
     return MPGNN_OK;

@@ -432,7 +432,11 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   const size_t smem = (size_t)tcw::kStagesW * (4 * tcw::kATileBytes + 2 * tcw::kRowsPerChunk * a.n * 4) +
                       (2 * tcw::kStagesW + 1) * 8 + 16;
   auto launch = [&](auto kernel) -> int {
-    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the opt-in limit is per function and process wide: always raise it to the device maximum, so that concurrent
+    // launches of the same kernel with different tile sizes (candidate trainers on several host threads) cannot
+    // lower it under one another
+    MPGNN_REQUIRE(smem <= (size_t)kMaxDynSmem, MPGNN_ENOTSUP, "shared memory request %zu exceeds the device limit", smem);
+    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kernel<<<grid, tcw::kThreadsW, smem, s>>>(p);
     MPGNN_LAUNCH_CHECK();
     return MPGNN_OK;

@@ -285,7 +285,11 @@ int launch_wgrad_tma(const GemmTnArgs& a, int grid, float* partials, int64_t par
   MPGNN_PROPAGATE(make_mn_tensor_map(&mg, a.b, a.m, a.ldb));
   const size_t smem = (size_t)tcw2::kStages * tcw2::kStageBytes + (3 * tcw2::kStages + 1) * 8 + 16;
   auto launch = [&](auto kernel) -> int {
-    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the opt-in limit is per function and process wide: always raise it to the device maximum, so that concurrent
+    // launches of the same kernel with different tile sizes (candidate trainers on several host threads) cannot
+    // lower it under one another
+    MPGNN_REQUIRE(smem <= (size_t)kMaxDynSmem, MPGNN_ENOTSUP, "shared memory request %zu exceeds the device limit", smem);
+    MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     kernel<<<grid, tcw2::kThreads, smem, s>>>(p, mh, mx, mg);
     MPGNN_LAUNCH_CHECK();
     return MPGNN_OK;
