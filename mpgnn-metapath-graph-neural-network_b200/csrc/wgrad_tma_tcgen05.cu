@@ -3,7 +3,7 @@
 // 4.36 ms against 3.85 ms for the LDG-fed kernel (3.98 ms when the raw tiles are used as the hi operands directly,
 // which the MMA's truncation of tf32 operands allows).  Kept because it establishes two facts the next version
 // needs: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B delivers exactly the UMMA MN-major tf32 layout, and the bound of this
-// kernel family is shared-memory traffic (operand reads + hi/lo writes), not the global loads -- see DESIGN.md 4.5.
+// kernel family is shared-memory traffic (operand reads + hi/lo writes), not the global loads -- see DESIGN.md 4.2.
 //
 //   D^T[128 x 256] = g_z^T [h | x]      rows of D^T = output columns n, columns = rows of [g_W ; g_root]
 //   colsum[128]    = sum_rows g_z        (g_bias)
