@@ -111,15 +111,21 @@ __global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, 
   base[(int64_t)k * bn + off] = v - hi;
 }
 
-// kDrop: 0 none, 1 seeded, 2 mask bits; kDeg: divide the first deg_cols columns by deg; kMasked: gate A by a_actmask
-template <int kDrop, bool kDeg, bool kMasked>
+// kDrop: 0 none, 1 seeded, 2 mask bits; kDeg: divide the first deg_cols columns by deg; kMasked: gate A by a_actmask.
+// kPair: CTA pairs (clusters of 2, tcgen05 cta_group::2).  The pair owns a 256-row tile and a BN-column slice: each CTA
+// streams and converts ITS 128 rows once, keeps HALF of the B slice (BN/2 columns) in shared memory, and the leader's
+// MMA thread issues M256 x N(BN) x K8 MMAs that read both halves -- for K = 256 (forward) this is what lets one pass
+// over A produce all 128 output columns instead of two CTAs converting the same tile for 64 columns each.
+template <int kDrop, bool kDeg, bool kMasked, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_a1,
                                                                    const __grid_constant__ CUtensorMap tmap_a2,
                                                                    const __grid_constant__ CUtensorMap tmap_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int K = p.k1 + p.k2;
-  const int BN = p.bn;
-  const int b_bytes = K * BN * 4;                         // one of hi / lo
+  const int BN = p.bn;                                    // accumulator width
+  const int BNB = kPair ? BN / 2 : BN;                    // B columns resident in THIS CTA
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const int b_bytes = K * BNB * 4;                        // one of hi / lo
   uint8_t* sm_b_hi = smem;
   uint8_t* sm_b_lo = smem + b_bytes;
   uint8_t* sm_raw = smem + 2 * b_bytes;                   // kRawStages raw chunks, 1024-byte aligned (swizzle)
@@ -135,21 +141,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   const uint32_t bar_rfull = smem_u32(bars + 2 * kStages + 4), bar_rempty = smem_u32(bars + 2 * kStages + 4 + kRawStages);
 
   // static work split: this CTA owns slice `slice` and row tiles group, group+n_groups, ...
-  const int slice = blockIdx.x % p.n_slices;
-  const int group = blockIdx.x / p.n_slices;
-  const int n_groups = gridDim.x / p.n_slices;
-  const int64_t n_tiles = (p.m + kTileM - 1) / kTileM;
+  // (pairs: "unit" = cluster, its tiles are 256 rows of which this CTA takes the half `rank`)
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int slice = unit % p.n_slices;
+  const int group = unit / p.n_slices;
+  const int n_groups = n_units / p.n_slices;
+  const int64_t n_tiles = kPair ? (p.m + 2 * kTileM - 1) / (2 * kTileM) : (p.m + kTileM - 1) / kTileM;
   const int my_tiles = (group < n_tiles) ? (int)((n_tiles - group + n_groups - 1) / n_groups) : 0;
+  // first row of this CTA's part of tile index t
+  auto tile_row0 = [&](int64_t t) -> int64_t { return kPair ? (t * 2 + rank) * kTileM : t * kTileM; };
   const int kch = K / kChunkK;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar_full + 8 * s, kConvGroupWarps);
+      mbar_init(bar_full + 8 * s, kPair ? 2 * kConvGroupWarps : kConvGroupWarps);   // pairs: both CTAs arrive on the leader's
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, kEpiWarps);
+      mbar_init(bar_tempty + 8 * b, kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int r = 0; r < kRawStages; ++r) {
       mbar_init(bar_rfull + 8 * r, 1);                 // one arrive.expect_tx + the TMA's byte count
@@ -159,13 +170,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   }
   if (warp == kMmaWarp) {  // TMEM: two fp32 accumulators of BN columns + kStages A stages (hi|lo)
     const uint32_t ncols = 512;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   {  // resident B slice (already in UMMA layout in global memory): straight 16-byte copies
-    const uint4* src = reinterpret_cast<const uint4*>(p.b_img + (int64_t)slice * 2 * K * BN);
+    // images are laid out per BNB-column slice: [slice][hi | lo][K * BNB]; a pair's CTA `rank` takes half `rank`
+    const int img = kPair ? slice * 2 + (int)rank : slice;
+    const uint4* src = reinterpret_cast<const uint4*>(p.b_img + (int64_t)img * 2 * K * BNB);
     uint4* dst = reinterpret_cast<uint4*>(sm_b_hi);
     const int n16 = 2 * b_bytes / 16;
     for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
@@ -174,9 +192,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();        // the peer's barriers and TMEM exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_a = tmem_base + (uint32_t)(2 * BN);   // A stages live after the two accumulators
+  // barriers the two CTAs of a pair share live in the leader (rank 0)
+  const uint32_t bar_full_l = kPair ? mapa_rank(bar_full, 0) : bar_full;
+  const uint32_t bar_tempty_l = kPair ? mapa_rank(bar_tempty, 0) : bar_tempty;
 
   if (warp < kProducerWarps) {
     // ================================ A converters (raw smem -> hi/lo -> TMEM) ===========
@@ -197,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     int mc = grp, mtile = 0;
     auto load_mask_word = [&]() -> uint32_t {
       while (mc >= kch) { mc -= kch; ++mtile; }
-      const int64_t grow = (int64_t)(group + (int64_t)mtile * n_groups) * kTileM + row;
+      const int64_t grow = tile_row0(group + (int64_t)mtile * n_groups) + row;
       const uint32_t w = grow < p.m ? __ldg(p.a_actmask + grow * kch + mc) : 0u;
       mc += kConvGroups;
       return w;
@@ -250,7 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         tc_fence_before();
         if (TC_EXP(32)) __nanosleep(500);
           __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster_after(bar_full_l + 8 * s, 0u);
+          else mbar_arrive(bar_full + 8 * s);
+        }
         TC_ACC(c_st);
       }
     }
@@ -278,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int buf = ti & 1;
       const uint32_t ph = (uint32_t)((ti >> 1) & 1);
-      const int64_t row0 = (int64_t)(group + (int64_t)ti * n_groups) * kTileM;
+      const int64_t row0 = tile_row0(group + (int64_t)ti * n_groups);
       const int64_t row = row0 + quarter * 32 + lane;       // the TMEM lane this thread reads
       float inv_deg = 1.f;
       if (kDeg && row < p.m) {
@@ -300,7 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
           __syncwarp();
           // data-dependent on the loaded registers: the MMA warp overwrites the accumulator as soon as the
           // barrier flips, so the LDTM must have delivered (see mbar_arrive_after)
-          if (lane == 0) mbar_arrive_after(bar_tempty + 8 * buf, v[0] | v[31]);
+          if (lane == 0) {
+            if (kPair) mbar_arrive_cluster_after(bar_tempty_l + 8 * buf, v[0] | v[31]);
+            else mbar_arrive_after(bar_tempty + 8 * buf, v[0] | v[31]);
+          }
         }
         if (TC_EXP(1)) continue;
         const int lcol0 = cc * kEpiCols;                    // column inside the slice
@@ -375,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         const bool first = kbase < p.k1;
         const CUtensorMap* map = first ? &tmap_a1 : &tmap_a2;
         const int kcoord = first ? kbase : kbase - p.k1;
-        const int64_t row0 = (int64_t)(group + (int64_t)tile_i * n_groups) * kTileM;
+        const int64_t row0 = tile_row0(group + (int64_t)tile_i * n_groups);
         const uint32_t dst = smem_u32(sm_raw + (size_t)rs * kRawBytes);
         const uint32_t bar = bar_rfull + 8 * rs;
         if (TC_EXP(8)) {
@@ -400,8 +428,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     // ONE elected thread runs the whole loop (the per-chunk elect + reconvergence cost ~100 cycles of the
     // serial issue path); it commits the "stage free" barrier once per PAIR of chunks: a tcgen05.commit
     // holds the issuing thread for 130-240 cycles, as long as the MMAs of half a chunk.
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc(kTileM, BN);
+    if (rank == 0 && elect_one()) {          // pairs: the leader issues for both CTAs
+      const uint32_t idesc = make_idesc(kPair ? 2 * kTileM : kTileM, BN);
       const uint32_t b_sbo = (uint32_t)(K / 4) * 128;
       const uint32_t bh_lo0 = desc_lo(smem_u32(sm_b_hi)), bl_lo0 = desc_lo(smem_u32(sm_b_lo));
       int s = 0;
@@ -410,11 +438,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       for (int ti = 0; ti < my_tiles; ++ti) {
         const int buf = ti & 1;
         const uint32_t ph = (uint32_t)((ti >> 1) & 1);
-        { TC_T0(); mbar_wait(bar_tempty + 8 * buf, ph ^ 1u); TC_ACC(m_tempty); }
+        { TC_T0(); if (kPair) mbar_wait_cluster(bar_tempty + 8 * buf, ph ^ 1u); else mbar_wait(bar_tempty + 8 * buf, ph ^ 1u); TC_ACC(m_tempty); }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
         for (int c = 0; c < kch; ++c) {
-          { TC_T0(); mbar_wait(bar_full + 8 * s, sph); TC_ACC(m_full); }
+          { TC_T0(); if (kPair) mbar_wait_cluster(bar_full + 8 * s, sph); else mbar_wait(bar_full + 8 * s, sph); TC_ACC(m_full); }
           if (TC_EXP(256)) __nanosleep(500);
               tc_fence_after();
           TC_T0();
@@ -424,13 +452,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
           for (int j = 0; j < kChunkK / 8; ++j) {
             const uint64_t dbh = desc_make(bh_lo0 + boff + j * 16, b_sbo);
             const uint64_t dbl = desc_make(bl_lo0 + boff + j * 16, b_sbo);
+            if (kPair) {
+              umma_tf32_ts_pair(d_tmem, ah + j * 8, dbh, idesc, (c | j) != 0 ? 1u : 0u);
+              umma_tf32_ts_pair(d_tmem, al + j * 8, dbh, idesc, 1u);
+              umma_tf32_ts_pair(d_tmem, ah + j * 8, dbl, idesc, 1u);
+              continue;
+            }
             umma_tf32_ts(d_tmem, ah + j * 8, dbh, idesc, (c | j) != 0 ? 1u : 0u);
             if (TC_EXP(4)) continue;
             umma_tf32_ts(d_tmem, al + j * 8, dbh, idesc, 1u);
             umma_tf32_ts(d_tmem, ah + j * 8, dbl, idesc, 1u);
           }
-          if (kPairShift == 0 || (s & 1)) umma_commit(bar_empty + 8 * (s >> kPairShift));   // stages s-1, s reusable once these MMAs have read them
-          if (c == kch - 1) umma_commit(bar_tfull + 8 * buf);   // accumulator complete
+          // stages s-1, s reusable once these MMAs have read them; accumulator complete after the tile's last chunk
+          if (kPair) {
+            if (kPairShift == 0 || (s & 1)) umma_commit_pair(bar_empty + 8 * (s >> kPairShift));
+            if (c == kch - 1) umma_commit_pair(bar_tfull + 8 * buf);
+          } else {
+            if (kPairShift == 0 || (s & 1)) umma_commit(bar_empty + 8 * (s >> kPairShift));
+            if (c == kch - 1) umma_commit(bar_tfull + 8 * buf);
+          }
           TC_ACC(m_issue);
           if (++s == kStages) { s = 0; sph ^= 1u; }
         }
@@ -446,10 +486,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();      // the peer may still be arriving on our barriers / the MMAs reading our smem
   if (warp == kMmaWarp) {
     tc_fence_after();
     const uint32_t ncols = 512;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
   }
 }
 
@@ -517,9 +559,18 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   MPGNN_REQUIRE(al16(a.a1) && (a.k2 == 0 || al16(a.a2)) && al16(a.out) && a.lda1 % 4 == 0 &&
                     (a.k2 == 0 || a.lda2 % 4 == 0) && a.ldo % 4 == 0,
                 MPGNN_EINVAL, "proj_tcgen05: operands must be 16-byte aligned with strides multiple of 4");
-  const int bn = pick_bn(k, a.n);
+  int bn = pick_bn(k, a.n);
+  // CTA pairs when a 128-column B slice does not fit one CTA (K > 128, i.e. the forward's [h | x] operand) but its
+  // halves do: the pair converts each A tile once for all 128 columns.  Opt-in (MPGNN_PROJ_PAIR=1): correct and
+  // tested, but at C4 it runs at the single-CTA kernel's 3.6 ms -- with the conversions halved the stage loop
+  // (converter -> remote arrive -> MMA -> multicast commit -> converter) is what bounds it, see DESIGN.md 4.2.
+  static const bool pair_ok = getenv("MPGNN_PROJ_PAIR") != nullptr && atoi(getenv("MPGNN_PROJ_PAIR")) != 0;
+  const bool pair = pair_ok && bn == 64 && a.n % 128 == 0 && k * 64 * 8 <= tc::kMaxBBytes && a.a1_actmask == nullptr &&
+                    a.deg_ptr == nullptr;
+  const int bnb = pair ? 64 : bn;              // B columns resident per CTA
+  if (pair) bn = 128;
   const int n_slices = (int)(a.n / bn);
-  tc::prep_b_images_kernel<<<(unsigned)ceil_div(k * a.n, 256), 256, 0, s>>>(a.b, (int)k, (int)a.n, bn, b_img);
+  tc::prep_b_images_kernel<<<(unsigned)ceil_div(k * a.n, 256), 256, 0, s>>>(a.b, (int)k, (int)a.n, bnb, b_img);
   MPGNN_LAUNCH_CHECK();
   tc::Params p{};
   p.a1 = a.a1; p.lda1 = a.lda1; p.k1 = (int)a.k1;
@@ -535,10 +586,12 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
 #ifdef MPGNN_TC_EXPERIMENT
   p.exp = getenv("MPGNN_TC_EXP") ? atoi(getenv("MPGNN_TC_EXP")) : 0;
 #endif
-  const int64_t n_tiles = ceil_div(a.m, tc::kTileM);
-  int64_t grid = n_tiles * n_slices;
-  if (grid > kNumSMs) grid = (kNumSMs / n_slices) * n_slices;
-  const size_t smem = (size_t)2 * k * bn * 4 + (size_t)tc::kRawStages * tc::kRawBytes +
+  const int64_t n_tiles = ceil_div(a.m, pair ? 2 * tc::kTileM : tc::kTileM);
+  int64_t grid = n_tiles * n_slices;           // work units: CTAs, or clusters of two
+  const int64_t max_units = pair ? kNumSMs / 2 : kNumSMs;
+  if (grid > max_units) grid = (max_units / n_slices) * n_slices;
+  if (pair) grid *= 2;
+  const size_t smem = (size_t)2 * k * bnb * 4 + (size_t)tc::kRawStages * tc::kRawBytes +
                       (size_t)tc::kEpiWarps * tc::kStgBytes + 128 * 4 +
                       (2 * tc::kStages + 4 + 2 * tc::kRawStages) * 8 + 16;
   CUtensorMap map1, map2, map_out;
@@ -552,6 +605,21 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
     // lower it under one another
     MPGNN_REQUIRE(smem <= (size_t)kMaxDynSmem, MPGNN_ENOTSUP, "shared memory request %zu exceeds the device limit", smem);
     MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    if (pair) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(tc::kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr{};
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      MPGNN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p, map1, map2, map_out));
+      count_launch();
+      return MPGNN_OK;
+    }
     kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p, map1, map2, map_out);
     MPGNN_LAUNCH_CHECK();
     return MPGNN_OK;
@@ -560,6 +628,13 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   if (p.a_actmask != nullptr) {
     MPGNN_REQUIRE(p.dropout_mode == 0, MPGNN_ENOTSUP, "proj_tcgen05: operand mask with a dropout epilogue");
     return deg ? launch(tc::gemm_rows_tc_kernel<0, true, true>) : launch(tc::gemm_rows_tc_kernel<0, false, true>);
+  }
+  if (pair) {
+    switch (p.dropout_mode) {
+      case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false, true>);
+      case 1: return launch(tc::gemm_rows_tc_kernel<1, false, false, true>);
+      default: return launch(tc::gemm_rows_tc_kernel<2, false, false, true>);
+    }
   }
   switch (p.dropout_mode * 2 + (deg ? 1 : 0)) {
     case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false>);

@@ -44,6 +44,63 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// ---- CTA pairs (cta_group::2): rank in the cluster, the peer's view of a barrier, cluster-scope arrive / wait ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {   // shared::cta address -> shared::cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// arrive on a barrier of (possibly) the other CTA of the cluster, data-dependent on `dep` like mbar_arrive_after
+__device__ __forceinline__ void mbar_arrive_cluster_after(uint32_t cluster_addr, uint32_t dep) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 t;\n\t"
+      "sub.u32 t, %1, 1;\n\t"
+      "and.b32 t, t, %1;\n\t"
+      "and.b32 t, t, 1;\n\t"
+      "shl.b32 t, t, 3;\n\t"
+      "add.u32 t, t, %0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [t];\n\t"
+      "}" ::"r"(cluster_addr), "r"(dep)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // arrivals may come from the peer CTA
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE_C;\n\t"
+      "bra WAIT_LOOP_C;\n\t"
+      "WAIT_DONE_C:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// cta_group::2 flavours: the MMA spans the two CTAs (M = 256), commits arrive on the barrier in both
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
