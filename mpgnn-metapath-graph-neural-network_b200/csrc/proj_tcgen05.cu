@@ -40,13 +40,13 @@ namespace tc {
 
 constexpr int kTileM = 128;
 constexpr int kChunkK = 32;                       // fp32 elements per pipeline stage (4 MMA K-steps)
-constexpr int kStages = 4;                        // TMEM A stages in flight (64 columns each)
+constexpr int kStages = 6;                        // capacity of the TMEM A-stage ring (64 columns each); p.n_stages are used
 constexpr int kRawStages = 4;                     // TMA-filled raw fp32 chunks in flight
 constexpr int kProducerWarps = 16;
 constexpr int kPairShift = 1;                                     // stage-free barrier shared by 2^kPairShift stages
 constexpr int kConvGroups = 2;                                    // converter groups taking alternate chunks
 constexpr int kConvGroupWarps = kProducerWarps / kConvGroups;     // 8: 4 TMEM lane quarters x 2 halves of the 32 K-columns
-static_assert(kStages == kRawStages && (kStages & (kStages - 1)) == 0 && kStages % kConvGroups == 0, "ring geometry");
+static_assert((kRawStages & (kRawStages - 1)) == 0 && kRawStages % kConvGroups == 0 && kStages % 2 == 0, "ring geometry");
 constexpr int kEpiWarps = 8;
 // Warp roles by warp id: producers first, epilogue warps next (id % 4 = TMEM lane quarter;
 // kProducerWarps is a multiple of 4), the single MMA-issuing warp last.
@@ -71,6 +71,8 @@ struct Params {
   const uint8_t* mask_bits; const uint64_t* offset_ptr;
   float* out; int64_t ldo;
   uint32_t* actmask_out;                       // [m][n/32] words, bit j of word c = [out(row, 32c+j) > 0]
+  int n_stages;   // TMEM A stages in use (even, <= kStages): 512 columns = acc_bufs * bn + 64 * n_stages
+  int acc_bufs;   // TMEM accumulators: 2 (double buffered) or 1 (released right after the epilogue's tcgen05.ld)
   const uint32_t* a_actmask; float a_scale;    // A(r,k) := bit(r,k) ? A(r,k)*a_scale : 0 ([m][K/32] words, k2 == 0)
 #ifdef MPGNN_TC_EXPERIMENT
   int exp;   // profiling build only (scripts/exp_variants.sh): bits switch pipeline stages off; results are WRONG
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   if (kPair) cluster_sync_all();        // the peer's barriers and TMEM exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_a = tmem_base + (uint32_t)(2 * BN);   // A stages live after the two accumulators
+  const uint32_t tmem_a = tmem_base + (uint32_t)(p.acc_bufs * BN);   // A stages live after the accumulator(s)
   // barriers the two CTAs of a pair share live in the leader (rank 0)
   const uint32_t bar_full_l = kPair ? mapa_rank(bar_full, 0) : bar_full;
   const uint32_t bar_tempty_l = kPair ? mapa_rank(bar_tempty, 0) : bar_tempty;
@@ -226,12 +228,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     };
     uint32_t mw = (kMasked && grp < total) ? load_mask_word() : 0u;
     long long c_rfull = 0, c_empty = 0, c_st = 0, c_total = TC_NOW();
+    int s = grp;                    // TMEM stage of chunk `it` (it % n_stages) and the parity of this use of it
+    uint32_t ph = 0;
     for (int it = grp; it < total; it += kConvGroups) {
-      const int s = it & (kStages - 1);
-      const uint32_t ph = (uint32_t)(it / kStages) & 1u;       // parity of this use of raw stage s / TMEM stage s
-      const uint8_t* tile = sm_raw + (size_t)s * kRawBytes;
+      const int rs = it & (kRawStages - 1);                    // raw stage and the parity of this use of it
+      const uint32_t rph = (uint32_t)(it / kRawStages) & 1u;
+      const uint8_t* tile = sm_raw + (size_t)rs * kRawBytes;
       const uint32_t mw_next = (kMasked && it + kConvGroups < total) ? load_mask_word() : 0u;
-      { TC_T0(); mbar_wait(bar_rfull + 8 * s, ph); TC_ACC(c_rfull); }   // the TMA bytes of this chunk have landed
+      { TC_T0(); mbar_wait(bar_rfull + 8 * rs, rph); TC_ACC(c_rfull); }   // the TMA bytes of this chunk have landed
       if (TC_EXP(64)) __nanosleep(500);
       float vv[16];
 #pragma unroll
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       // one register of each of the four loads of every lane (cheaper than a proxy fence per chunk).
       uint32_t dep = __float_as_uint(vv[0]) | __float_as_uint(vv[4]) | __float_as_uint(vv[8]) | __float_as_uint(vv[12]);
       dep = __reduce_or_sync(0xFFFFFFFFu, dep);
-      if (lane == 0) mbar_arrive_after(bar_rempty + 8 * s, dep);   // raw stage may be refilled
+      if (lane == 0) mbar_arrive_after(bar_rempty + 8 * rs, dep);   // raw stage may be refilled
       if (kMasked) {
         const uint32_t bits = mw >> (colhalf * 16);
 #pragma unroll
@@ -278,6 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         }
         TC_ACC(c_st);
       }
+      s += kConvGroups;
+      if (s >= p.n_stages) { s -= p.n_stages; ph ^= 1u; }
     }
     if (warp == 0 || warp == kConvGroupWarps) {
       const int role = warp == 0 ? 0 : 1;
@@ -301,8 +307,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     if (kDrop == 1) launch_key = dropout_launch_key(p.seed, p.offset + (p.offset_ptr != nullptr ? *p.offset_ptr : 0ull));
     long long e_tfull = 0, e_ld = 0, e_total = TC_NOW();
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int buf = ti & 1;
-      const uint32_t ph = (uint32_t)((ti >> 1) & 1);
+      const int buf = p.acc_bufs == 2 ? (ti & 1) : 0;
+      const uint32_t ph = (uint32_t)((p.acc_bufs == 2 ? (ti >> 1) : ti) & 1);
       const int64_t row0 = tile_row0(group + (int64_t)ti * n_groups);
       const int64_t row = row0 + quarter * 32 + lane;       // the TMEM lane this thread reads
       float inv_deg = 1.f;
@@ -436,8 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       uint32_t sph = 0;
       long long m_tempty = 0, m_full = 0, m_issue = 0, m_total = TC_NOW();
       for (int ti = 0; ti < my_tiles; ++ti) {
-        const int buf = ti & 1;
-        const uint32_t ph = (uint32_t)((ti >> 1) & 1);
+        const int buf = p.acc_bufs == 2 ? (ti & 1) : 0;
+        const uint32_t ph = (uint32_t)((p.acc_bufs == 2 ? (ti >> 1) : ti) & 1);
         { TC_T0(); if (kPair) mbar_wait_cluster(bar_tempty + 8 * buf, ph ^ 1u); else mbar_wait(bar_tempty + 8 * buf, ph ^ 1u); TC_ACC(m_tempty); }
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
             if (c == kch - 1) umma_commit(bar_tfull + 8 * buf);
           }
           TC_ACC(m_issue);
-          if (++s == kStages) { s = 0; sph ^= 1u; }
+          if (++s == p.n_stages) { s = 0; sph ^= 1u; }
         }
       }
 #ifdef MPGNN_TC_COUNTERS
@@ -583,6 +589,12 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits; p.offset_ptr = a.offset_ptr;
   p.out = a.out; p.ldo = a.ldo;
   p.actmask_out = a.actmask_out; p.a_actmask = a.a1_actmask; p.a_scale = a.a1_scale;
+  // TMEM budget (512 columns): two accumulators + as many 64-column A stages as fit: six at BN = 64 (measured:
+  // forward 3.81 -> 3.59 ms against four), four at BN = 128 (one accumulator + six stages was slower: 3.39 -> 3.85 ms)
+  p.acc_bufs = 2;
+  p.n_stages = (512 - p.acc_bufs * bn) / tc::kACols;
+  if (p.n_stages > tc::kStages) p.n_stages = tc::kStages;
+  p.n_stages &= ~1;
 #ifdef MPGNN_TC_EXPERIMENT
   p.exp = getenv("MPGNN_TC_EXP") ? atoi(getenv("MPGNN_TC_EXP")) : 0;
 #endif
