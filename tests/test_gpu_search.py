@@ -93,3 +93,40 @@ def test_greedy_search_step0_end_to_end(fx3):
     assert res["kept"] == g["step0_best"].tolist()              # bit-exact selection
     assert set(res["final_dict"]) == {"[0]", "[1]"} and all(0.0 <= v <= 1.0 for v in res["final_dict"].values())
     assert res["final_meta"] and res["final_meta"][0] in ([0], [1]) and 0.5 < res["test_f1"] <= 1.0
+
+
+def test_k5_scorer_fb15k237_shape_with_source_mask_matches_oracle():
+    """BASELINE configs[2] shape (14,541 entities, 237 relations, 272,115 edges; 4,530 labelled sources as in `sn`,
+    main.py:357-364): the scorer restricted to the labelled sources, against the oracle for the three most frequent
+    relations."""
+    gen = torch.Generator().manual_seed(237)
+    n, e, r = 14541, 272115, 237
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    et = (torch.rand(e, generator=gen) ** 3 * r).long().clamp_(max=r - 1)          # skewed relation frequencies
+    lab = (torch.rand(n, generator=gen) < 0.22).long()
+    labelled = torch.randperm(n, generator=gen)[:4530]
+    mask = torch.zeros(n, dtype=torch.uint8)
+    mask[labelled] = 1
+    graph = mpgnn_b200.RelationGraph(ei, et, n, r, device=DEV)
+    for rel in torch.bincount(et, minlength=r).argsort(descending=True)[:3].tolist():
+        w0 = torch.rand(n, generator=gen)
+        traj, w, arg = search.run_scorer(graph, rel, w0, lab.float(), source_mask=mask, epochs=25)
+        # oracle restatement of the same loop on the masked sources (main.py:919-1010 with source_nodes_mask)
+        rows, cols = ei[0][et == rel], ei[1][et == rel]
+        wt = w0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([wt], lr=0.1)
+        srcs = torch.unique(rows[mask[rows].bool()])
+        ref = []
+        for _ in range(25):
+            opt.zero_grad()
+            pred = torch.zeros(n)
+            vals = torch.full((n,), -1.0).scatter_reduce(0, rows, wt[cols], reduce="amax", include_self=True)
+            pred[srcs] = vals[srcs]
+            sel = mask.bool()
+            loss = ((pred[sel] - lab.float()[sel]) ** 2).mean()
+            loss.backward()
+            opt.step()
+            with torch.no_grad():
+                wt.clamp_(0.0, 1.0)
+            ref.append(float(loss))
+        assert np.allclose(traj.numpy()[:1], ref[:1], rtol=1e-5, atol=1e-8), (rel, traj[:3], ref[:3])
