@@ -44,11 +44,11 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the same command
-# (profiles/r01_tc6_ncu.md); None where no capture exists.
+# (profiles/r01_final_ncu.md); None where no capture exists.
 NCU_TRAFFIC = {
-    "proj_fwd_tcgen05": 10.240e9 + 5.249e9,       # profiles/r01_tc6_ncu.md
-    "dgrad_nt_tcgen05": 5.321e9 + 10.191e9,       # profiles/r01_tc6_ncu.md
-    "wgrad_tn_tcgen05": 15.527e9 + 0.013e9,       # profiles/r01_tc5_ncu.md
+    "proj_fwd_tcgen05": 10.277e9 + 5.250e9,       # profiles/r01_final_ncu.md
+    "wgrad_tn_tcgen05": 15.539e9 + 0.022e9,       # profiles/r01_final_ncu.md
+    "dgrad_nt_tcgen05": 5.321e9 + 10.186e9,       # profiles/r01_final_ncu.md
     "spmm_mean_fwd": 6.77e9,                      # profiles/r01_simt_ncu.md
 }
 

@@ -8,6 +8,6 @@ $CMD > gpurun_out/ncu_plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list_${TAG}.log 2>&1
 echo "launch list exit: $?"
 $CMD > gpurun_out/ncu_plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 2 -c 2 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 3 -c 3 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full capture exit: $?"
 ls -la gpurun_out | tail -12
