@@ -1,3 +1,4 @@
+# repeated tcgen05-vs-fp32 forward on shapes that exposed the raw-ring race; prints bad elements/rows per trial
 import sys, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import mpgnn_b200
