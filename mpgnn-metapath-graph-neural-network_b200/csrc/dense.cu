@@ -276,11 +276,25 @@ __global__ void __launch_bounds__(TN_THREADS) gemm_tn_kernel(GemmTnArgs a, int64
   }
 }
 
-__global__ void gemm_tn_reduce_kernel(GemmTnArgs a, int64_t ktot, int64_t splits) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ktot * a.n) return;
+// Second pass: one warp per 32 consecutive outputs and kTnRedSeg warps per block, each summing a contiguous segment of
+// the splits (coalesced, independent loads in flight); the segment sums are combined in segment order, so the summation
+// tree is a function of (splits) only -- the same on every run.
+constexpr int kTnRedSeg = 8;
+__global__ void __launch_bounds__(32 * kTnRedSeg) gemm_tn_reduce_kernel(GemmTnArgs a, int64_t ktot, int64_t splits) {
+  __shared__ float seg_sum[kTnRedSeg][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t total = ktot * a.n;
+  const int64_t s0 = splits * seg / kTnRedSeg, s1 = splits * (seg + 1) / kTnRedSeg;
+  float part = 0.f;
+  if (i < total)
+    for (int64_t sp = s0; sp < s1; ++sp) part += a.partials[sp * total + i];
+  seg_sum[seg][lane] = part;
+  __syncthreads();
+  if (seg != 0 || i >= total) return;
   float s = 0.f;
-  for (int64_t sp = 0; sp < splits; ++sp) s += a.partials[sp * ktot * a.n + i];  // fixed order
+#pragma unroll
+  for (int k = 0; k < kTnRedSeg; ++k) s += seg_sum[k][lane];
   const int64_t kr = i / a.n, nc = i % a.n;
   if (kr < a.k1) {
     if (a.out1) a.out1[kr * a.ldo1 + nc] = s;
@@ -377,7 +391,7 @@ int launch_gemm_tn(const GemmTnArgs& a, cudaStream_t s) {
   }
   MPGNN_LAUNCH_CHECK();
   const int64_t total = ktot * a.n;
-  gemm_tn_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(a, ktot, splits);
+  gemm_tn_reduce_kernel<<<(unsigned)ceil_div(total, 32), 32 * kTnRedSeg, 0, s>>>(a, ktot, splits);
   MPGNN_LAUNCH_CHECK();
   return MPGNN_OK;
 }

@@ -161,12 +161,17 @@ def test_hop_fused_epilogue_matches_oracle(n, e, r, f_in, f_out):
     rel = int(torch.bincount(et, minlength=r).argmax()) if r > 64 else r - 1     # a populated relation of the big one
     z, h, cnt = orc.conv_forward(x, ei, et, rel, w, root, b)
     y_ref = torch.relu(z) * mask * 2.5
-    gz = gy * (y_ref > 0) * 2.5
-    gx_ref, gw_ref, gr_ref, gb_ref = orc.conv_backward(x, ei, et, rel, w, root, h, cnt, gz)
     xi = x.to(DEV).requires_grad_(True)
     y = conv.hop(rel, xi, graph, relu=True, dropout_p=0.6, dropout_mask=mask)
     y.backward(gy.to(DEV))
     assert rel_err(y, y_ref) < FP32_TOL
+    # the backward is compared on the device's own activation pattern: an element with |z| ~ 1e-8 may sit on either
+    # side of the ReLU in two correct fp32 evaluations (the CPU matmul is not bit-reproducible run to run), and one
+    # flipped gate moves g_x by far more than the tolerance
+    act = y.detach().cpu() > 0
+    assert bool(((act != (y_ref > 0)) <= (z.abs() < 1e-5)).all())
+    gz = gy * act * 2.5
+    gx_ref, gw_ref, gr_ref, gb_ref = orc.conv_backward(x, ei, et, rel, w, root, h, cnt, gz)
     assert rel_err(xi.grad, gx_ref) < FP32_TOL
     assert rel_err(conv.weight.grad, gw_ref) < FP32_TOL
     assert rel_err(conv.root.grad, gr_ref) < FP32_TOL
