@@ -342,11 +342,12 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if precision == "fp32" else "f32 (3xTF32 split on tcgen05, fp32 accumulate; 1e-5 parity bar)",
+        "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "C4: %d nodes / %d edges / %d relations / hidden %d; step = 1 metapath hop fwd+bwd "
                                "(relu + dropout 0.6 fused, input gradient included), relations cycled" % (n, e, r, f),
-                   "l2": "inputs (5.12 GB per dense operand) larger than L2, no flush", "precision": precision,
+                   "l2": "inputs (5.12 GB per dense operand) larger than L2, no flush", "precision": precision if precision == "fp32" else
+                   "tf32x3: fp32 operands split hi+lo in TF32, three tcgen05 MMA passes, fp32 accumulate (1e-5 parity bar)",
                    "parallelism": "replicated graph, hops sharded by relation over %d GPU(s)" % world},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu,
