@@ -286,6 +286,7 @@ def run_ours(args):
                "ms_per_step": ms_e / e_steps}
 
     cand = None if args.no_candidates else candidate_scoring(rank, world, dev, dist)
+    rels = None if args.no_candidates else relation_scoring(rank, world, dev, dist)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -356,7 +357,7 @@ def run_ours(args):
                                    "note": "SURVEY 8(d): B_fwd (fused layer) + B_bwd + 8 N F for the materialised t"},
                   "graph_build_s": build_s, "rows_per_s": n * args.steps * world / (ms * 1e-3),
                   "mean_edges_per_hop": e_r_mean, "kernels": per_kernel, "spmm_mean_fwd_roofline": spmm_roof,
-                  "candidate_scoring": cand},
+                  "candidate_scoring": cand, "relation_scoring": rels},
     }
     emit(line)
 
@@ -415,6 +416,54 @@ def candidate_scoring(rank, world, dev, dist, per_rank=8):
         per_epoch = (time.time() - t1) / 3
         out["cpu_port_candidates_per_s_extrapolated"] = 1.0 / (per_epoch * epochs)
         out["cpu_port_note"] = "oracle port, 3 epochs timed on %d threads, linearly extrapolated to 999" % torch.get_num_threads()
+    return out
+
+
+def relation_scoring(rank, world, dev, dist):
+    """Search-stage throughput (relations scored/s): the step-0 scorer of main.py:919-1010 (100 epochs of
+    per-source argmax + MSE + Adam, K5) for every relation of a configs[4]-shaped graph (1M nodes, 100 relations,
+    ~3 out-edges per node), relations split over the ranks with the reference's np.array_split rule."""
+    import mpgnn_b200
+    from mpgnn_b200 import search
+    n, r = 1_000_000, 100
+    g = torch.Generator().manual_seed(2)
+    deg = torch.randint(1, 6, (n,), generator=g)
+    rows = torch.repeat_interleave(torch.arange(n), deg)
+    e = rows.numel()
+    cols = torch.randint(0, n, (e,), generator=g)
+    et = torch.randint(0, r, (e,), generator=g)
+    lab = torch.randint(0, 2, (n,), generator=g).float()
+    graph = mpgnn_b200.RelationGraph(torch.stack([rows, cols]), et, n, r, device=dev)
+    mine = search.relation_split(list(range(r)), world, rank)
+    w0 = torch.rand(n, generator=g)
+    search.run_scorer(graph, 0, w0, lab, epochs=5)                     # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    losses = [float(search.run_scorer(graph, rel, w0, lab)[0][-1]) for rel in mine]
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out = {"relations_per_s": r / dt, "relations": r, "seconds": dt, "epochs_per_relation": search.SCORER_EPOCHS,
+           "config": "configs[4] shape: %d nodes / %d edges / %d relations, random binary labels" % (n, e, r),
+           "final_loss_first_relation": losses[0] if losses else None}
+    if rank == 0 and world == 1:
+        from oracle import search_oracle as so
+        ei_np, et_np, lab_np = torch.stack([rows, cols]).numpy(), et.numpy(), lab.long().numpy()
+        t1 = time.time()
+        so.score_relation(ei_np, et_np, 0, lab_np, n, epochs=1)
+        one = time.time() - t1
+        t1 = time.time()
+        so.score_relation(ei_np, et_np, 0, lab_np, n, epochs=3)
+        three = time.time() - t1
+        per_epoch = max((three - one) / 2, 1e-9)
+        out["cpu_port_relations_per_s_extrapolated"] = 1.0 / (one - per_epoch + per_epoch * search.SCORER_EPOCHS)
+        out["cpu_port_note"] = ("oracle port, relation 0 of the same graph: dictionaries + 1 epoch %.2f s, %.3f s per further "
+                                "epoch, extrapolated to %d epochs" % (one, per_epoch, search.SCORER_EPOCHS))
     return out
 
 
