@@ -39,6 +39,7 @@ WORKLOADS = {
     # name: (nodes, edges, relations, feat)
     "c4": (10_000_000, 200_000_000, 64, 128),
     "c4_tenth": (1_000_000, 20_000_000, 64, 128),   # CPU-arm sample of the same shape
+    "c4_zipf": (10_000_000, 200_000_000, 64, 128),  # SURVEY 8d variant: message sources ~ Zipf(1) (hub columns)
     "tiny": (20_000, 400_000, 8, 128),              # plumbing check only
 }
 
@@ -144,6 +145,14 @@ def run_ours(args):
     # ---- synthetic graph of the named shape (seed 0), built once: the graph is a run constant
     gen = torch.Generator(device=dev).manual_seed(0)
     ei = torch.randint(0, n, (2, e), device=dev, generator=gen)
+    if args.workload == "c4_zipf":
+        # popularity of a message source ~ 1/rank (continuous Zipf, alpha = 1), hubs spread by a random relabelling:
+        # the transposed gather of the backward then meets columns with ~10^5 edges per relation
+        u = torch.rand(e, device=dev, generator=gen)
+        rank_k = torch.exp(u * float(np.log(n))).long().clamp_(1, n) - 1
+        perm = torch.randperm(n, device=dev, generator=gen)
+        ei[1] = perm[rank_k]
+        del u, rank_k, perm
     et = torch.randint(0, r, (e,), device=dev, generator=gen)
     torch.cuda.synchronize()
     t0 = time.time()

@@ -236,9 +236,7 @@ int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, 
                 (long long)relation, (long long)gi->r);
   MPGNN_REQUIRE(feat >= 1 && ldx >= feat && ldout >= feat && (!d_init || ldinit >= feat), MPGNN_EINVAL,
                 "spmm: bad strides");
-  const int32_t* ptr = (transpose ? gi->csc_ptr : gi->csr_ptr) + relation * gi->n;
-  const int32_t* idx = transpose ? gi->csc_idx : gi->csr_idx;
-  return launch_spmm(ptr, idx, gi->n, mean, d_x, ldx, feat, d_init, ldinit, d_out, ldout, stream_of(stream));
+  return launch_spmm_graph(gi, relation, transpose, mean, d_x, ldx, feat, d_init, ldinit, d_out, ldout, stream_of(stream));
 }
 
 int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t f_in, const float* d_w,

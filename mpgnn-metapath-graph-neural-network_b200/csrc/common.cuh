@@ -73,8 +73,22 @@ struct Workspace {
   }
 };
 
+// Buckets with more than kHeavyDeg edges ("hub" rows of a relation, e.g. popular message sources in the transposed
+// view of a power-law graph).  One warp walking such a bucket alone sets the duration of the whole aggregation, so
+// they are cut into chunks of kHeavyDeg edges summed by separate warps and combined in chunk order (fixed tree).
+// Found once per graph: the graph is a run constant.
+constexpr int kHeavyDeg = 256;
+struct HeavyRows {
+  int64_t count;             // heavy buckets over all relations
+  int32_t* rows;             // [count] node id of the bucket inside its relation, sorted by (relation, node)  (device)
+  int32_t* chunk_ptr;        // [count] first chunk of the bucket, counted inside its relation               (device)
+  int64_t* rel_ptr_host;     // [r+1] slice of rows / chunk_ptr belonging to each relation
+  int64_t* rel_chunks_host;  // [r]   chunks in each relation
+};
+
 struct mpgnn_graph_impl {
   int64_t n, e, r;
+  HeavyRows heavy[2];        // [0] CSR buckets (rel,row), [1] CSC buckets (rel,col)
   int32_t* csr_ptr;  // [r*n+1] bucket (rel,row) -> positions in csr_idx
   int32_t* csr_idx;  // [e] message source (col) of each edge, stable order
   int32_t* csr_eid;  // [e] original edge id
@@ -135,6 +149,9 @@ int launch_pack_actmask(const float* y, int64_t m, int64_t n, uint32_t* mask, cu
 int launch_relu_dropout_bwd_mask(const float* gy, const uint32_t* mask, float scale, float* gz, int64_t m, int64_t n,
                                  cudaStream_t s);
 
+// aggregation over relation `rel` of a graph handle (transpose = CSC view), hub buckets included
+int launch_spmm_graph(const mpgnn_graph_impl* g, int64_t rel, int transpose, int mean, const float* x, int64_t ldx,
+                      int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s);
 int launch_spmm(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
                 int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s);
 

@@ -5,6 +5,9 @@
 // key = relation*N + node with a stable LSD radix sort (8-bit digits, per-block digit
 // histograms, one global exclusive scan, stable in-block ranking), so bucket (r,i) lists
 // its edges in original edge order, duplicates kept.  Integer work, HBM bound, bit exact.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace mpgnn {
@@ -246,8 +249,96 @@ static int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b
   return MPGNN_OK;
 }
 
+// ---- hub buckets -------------------------------------------------------------------------------
+__global__ void count_heavy_kernel(const int32_t* __restrict__ ptr, int64_t buckets, unsigned long long* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < buckets && ptr[i + 1] - ptr[i] > kHeavyDeg) atomicAdd(count, 1ull);
+}
+__global__ void collect_heavy_kernel(const int32_t* __restrict__ ptr, int64_t buckets, unsigned long long* __restrict__ slot,
+                                     uint32_t* __restrict__ bucket_id, int32_t* __restrict__ deg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= buckets) return;
+  const int d = ptr[i + 1] - ptr[i];
+  if (d > kHeavyDeg) {
+    const unsigned long long k = atomicAdd(slot, 1ull);       // order fixed afterwards by a host sort
+    bucket_id[k] = (uint32_t)i;
+    deg[k] = d;
+  }
+}
+
+static void free_heavy(HeavyRows* h) {
+  cudaFree(h->rows);
+  cudaFree(h->chunk_ptr);
+  free(h->rel_ptr_host);
+  free(h->rel_chunks_host);
+  memset(h, 0, sizeof(*h));
+}
+
+// Lists the buckets of `ptr` ([r*n+1]) with more than kHeavyDeg edges: sorted by (relation, node), with the chunk
+// each one starts at inside its relation.  Called once per direction after the build (synchronises the stream).
+static int find_heavy(const int32_t* ptr, int64_t n, int64_t r, cudaStream_t s, HeavyRows* out) {
+  memset(out, 0, sizeof(*out));
+  out->rel_ptr_host = static_cast<int64_t*>(calloc(r + 1, sizeof(int64_t)));
+  out->rel_chunks_host = static_cast<int64_t*>(calloc(r, sizeof(int64_t)));
+  MPGNN_REQUIRE(out->rel_ptr_host && out->rel_chunks_host, MPGNN_ECUDA, "graph_build: host allocation failed");
+  const int64_t buckets = r * n;
+  unsigned long long* d_count = nullptr;
+  MPGNN_CUDA_CHECK(cudaMalloc(&d_count, sizeof(unsigned long long)));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
+  const unsigned blocks = (unsigned)ceil_div(buckets, 256);
+  count_heavy_kernel<<<blocks, 256, 0, s>>>(ptr, buckets, d_count);
+  unsigned long long h_count = 0;
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(&h_count, d_count, sizeof(h_count), cudaMemcpyDeviceToHost, s));
+  MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (h_count == 0) {
+    cudaFree(d_count);
+    return MPGNN_OK;
+  }
+  uint32_t* d_id = nullptr;
+  int32_t* d_deg = nullptr;
+  MPGNN_CUDA_CHECK(cudaMalloc(&d_id, h_count * 4));
+  MPGNN_CUDA_CHECK(cudaMalloc(&d_deg, h_count * 4));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
+  collect_heavy_kernel<<<blocks, 256, 0, s>>>(ptr, buckets, d_count, d_id, d_deg);
+  std::vector<uint32_t> ids(h_count);
+  std::vector<int32_t> degs(h_count);
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(ids.data(), d_id, h_count * 4, cudaMemcpyDeviceToHost, s));
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(degs.data(), d_deg, h_count * 4, cudaMemcpyDeviceToHost, s));
+  MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(d_count); cudaFree(d_id); cudaFree(d_deg);
+  std::vector<size_t> order(h_count);
+  for (size_t i = 0; i < h_count; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ids[a] < ids[b]; });
+  std::vector<int32_t> rows(h_count), chunk0(h_count);
+  int64_t cur_rel = -1, chunks = 0;
+  for (size_t k = 0; k < h_count; ++k) {
+    const uint32_t id = ids[order[k]];
+    const int64_t rel = id / n;
+    while (cur_rel < rel) {                       // close the relations up to `rel`
+      if (cur_rel >= 0) out->rel_chunks_host[cur_rel] = chunks;
+      ++cur_rel;
+      out->rel_ptr_host[cur_rel] = (int64_t)k;
+      chunks = 0;
+    }
+    rows[k] = (int32_t)(id % n);
+    chunk0[k] = (int32_t)chunks;
+    chunks += ceil_div((int64_t)degs[order[k]], kHeavyDeg);
+  }
+  if (cur_rel >= 0) out->rel_chunks_host[cur_rel] = chunks;
+  for (int64_t q = cur_rel + 1; q <= r; ++q) out->rel_ptr_host[q] = (int64_t)h_count;
+  MPGNN_CUDA_CHECK(cudaMalloc(&out->rows, h_count * 4));
+  MPGNN_CUDA_CHECK(cudaMalloc(&out->chunk_ptr, h_count * 4));
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(out->rows, rows.data(), h_count * 4, cudaMemcpyHostToDevice, s));
+  MPGNN_CUDA_CHECK(cudaMemcpyAsync(out->chunk_ptr, chunk0.data(), h_count * 4, cudaMemcpyHostToDevice, s));
+  MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
+  out->count = (int64_t)h_count;
+  return MPGNN_OK;
+}
+
 static void free_graph(mpgnn_graph_impl* g) {
   if (!g) return;
+  free_heavy(&g->heavy[0]);
+  free_heavy(&g->heavy[1]);
   cudaFree(g->csr_ptr);
   cudaFree(g->csr_idx);
   cudaFree(g->csr_eid);
@@ -357,6 +448,8 @@ int graph_build_device(const int64_t* d_edge_index, const int64_t* d_edge_type, 
   if (rc == MPGNN_OK)
     for (int64_t k = 0; k <= r; ++k) g->rel_offsets_host[k] = h_ptr_samples[k];
   free(h_ptr_samples);
+  if (rc == MPGNN_OK) rc = find_heavy(g->csr_ptr, n, r, s, &g->heavy[0]);
+  if (rc == MPGNN_OK) rc = find_heavy(g->csc_ptr, n, r, s, &g->heavy[1]);
   if (rc != MPGNN_OK) {
     free_graph(g);
     return rc;

@@ -55,7 +55,7 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   const int32_t* ptr = g->csr_ptr + rel * g->n;
   {
     ScopedTimer tm("spmm_mean_fwd", s);
-    MPGNN_PROPAGATE(launch_spmm(ptr, g->csr_idx, g->n, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));
+    MPGNN_PROPAGATE(launch_spmm_graph(g, rel, /*transpose=*/0, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));
   }
   MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp, w, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
   MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp + f_in * f_out, root, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
@@ -166,8 +166,7 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
     }
     // g_x[j] = (g_z root^T)[j] + sum_{e: col(e)=j} t[row(e)]
     ScopedTimer tm("spmm_transpose_bwd", s);
-    MPGNN_PROPAGATE(launch_spmm(g->csc_ptr + rel * n, g->csc_idx, n, /*mean=*/0, t, 2 * f_in, f_in, t + f_in,
-                                2 * f_in, gx, f_in, s));
+    MPGNN_PROPAGATE(launch_spmm_graph(g, rel, /*transpose=*/1, /*mean=*/0, t, 2 * f_in, f_in, t + f_in, 2 * f_in, gx, f_in, s));
   }
   return MPGNN_OK;
 }

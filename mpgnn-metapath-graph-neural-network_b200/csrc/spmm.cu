@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256) spmm_gather_kernel(const int32_t* __restr
                                                           const int32_t* __restrict__ idx, int64_t n_rows,
                                                           int mean, const float* __restrict__ x, int64_t ldx,
                                                           int units, const float* __restrict__ init,
-                                                          int64_t ldinit, float* __restrict__ out, int64_t ldout) {
+                                                          int64_t ldinit, float* __restrict__ out, int64_t ldout,
+                                                          int skip_deg) {
   using V = typename VecT<VEC>::type;
   constexpr int ROWS_PER_WARP = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) spmm_gather_kernel(const int32_t* __restr
       end = __ldg(ptr + row + 1);
     }
     const int deg = end - beg;
+    if (skip_deg > 0 && deg > skip_deg) continue;   // hub bucket: left to the chunked kernels (uniform per row group)
     for (int u0 = 0; u0 < units; u0 += LPR) {   // feature chunks (one pass when feat <= 32*VEC)
       const int u = u0 + sub;
       const bool u_ok = row_ok && u < units;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) spmm_gather_kernel(const int32_t* __restr
 
 template <int VEC, int LPR>
 static int launch_one(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
-                      int units, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
+                      int units, const float* init, int64_t ldinit, float* out, int64_t ldout, int skip_deg, cudaStream_t s) {
   constexpr int ROWS_PER_WARP = 32 / LPR;
   const int64_t n_groups = ceil_div(n_rows, ROWS_PER_WARP);
   const int64_t blocks_needed = ceil_div(n_groups, 8);  // 8 warps per block
@@ -132,17 +134,18 @@ static int launch_one(const int32_t* ptr, const int32_t* idx, int64_t n_rows, in
   if (blocks > kNumSMs) blocks = (blocks / kNumSMs) * kNumSMs;
   if (blocks < 1) blocks = 1;
   spmm_gather_kernel<VEC, LPR><<<(unsigned)blocks, 256, 0, s>>>(ptr, idx, n_rows, mean, x, ldx, units, init, ldinit,
-                                                             out, ldout);
+                                                             out, ldout, skip_deg);
   MPGNN_LAUNCH_CHECK();
   return MPGNN_OK;
 }
 
 template <int VEC>
 static int launch_vec(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
-                      int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
+                      int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, int skip_deg,
+                      cudaStream_t s) {
   const int units = (int)(feat / VEC);
 #define MPGNN_SPMM_CASE(L) \
-  return launch_one<VEC, L>(ptr, idx, n_rows, mean, x, ldx, units, init, ldinit, out, ldout, s)
+  return launch_one<VEC, L>(ptr, idx, n_rows, mean, x, ldx, units, init, ldinit, out, ldout, skip_deg, s)
   if (units <= 1) MPGNN_SPMM_CASE(1);
   if (units <= 2) MPGNN_SPMM_CASE(2);
   if (units <= 4) MPGNN_SPMM_CASE(4);
@@ -152,10 +155,119 @@ static int launch_vec(const int32_t* ptr, const int32_t* idx, int64_t n_rows, in
 #undef MPGNN_SPMM_CASE
 }
 
+
 static bool aligned_to(const void* p, int64_t bytes) { return (reinterpret_cast<uintptr_t>(p) % bytes) == 0; }
+
+static int launch_spmm_skip(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
+                            int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, int skip_deg,
+                            cudaStream_t s);
 
 int launch_spmm(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
                 int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
+  return launch_spmm_skip(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, 0, s);
+}
+
+// ---- hub buckets: chunked partial sums + fixed-order finish -----------------------------------------------------
+// One warp per chunk of kHeavyDeg edges (lane u covers 128-bit slots u, u+32, ...): partial[c][:] = sum of the chunk's
+// gathered rows in bucket order.
+__global__ void __launch_bounds__(256) spmm_heavy_chunk_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                               const int32_t* __restrict__ rows,
+                                                               const int32_t* __restrict__ chunk_ptr, int n_heavy,
+                                                               int64_t n_chunks, const float* __restrict__ x, int64_t ldx,
+                                                               int units, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp_id; c < n_chunks; c += n_warps) {
+    int lo = 0, hi = n_heavy - 1;                  // last heavy bucket whose first chunk is <= c
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(chunk_ptr + mid) <= c) lo = mid; else hi = mid - 1;
+    }
+    const int32_t row = __ldg(rows + lo);
+    const int32_t beg = __ldg(ptr + row) + (int32_t)(c - __ldg(chunk_ptr + lo)) * kHeavyDeg;
+    const int32_t end = min(__ldg(ptr + row + 1), beg + kHeavyDeg);
+    for (int u0 = 0; u0 < units; u0 += 32) {
+      const int u = u0 + lane;
+      const bool u_ok = u < units;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int32_t b = beg; b < end; b += 32) {
+        const int32_t my = (b + lane < end) ? __ldg(idx + b + lane) : 0;
+        const int cnt = min(32, end - b);
+        int k = 0;
+        for (; k + 4 <= cnt; k += 4) {
+          const int32_t c0 = __shfl_sync(0xffffffffu, my, k), c1 = __shfl_sync(0xffffffffu, my, k + 1);
+          const int32_t c2 = __shfl_sync(0xffffffffu, my, k + 2), c3 = __shfl_sync(0xffffffffu, my, k + 3);
+          if (u_ok) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c0 * ldx + (int64_t)u * 4));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c1 * ldx + (int64_t)u * 4));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c2 * ldx + (int64_t)u * 4));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c3 * ldx + (int64_t)u * 4));
+            vadd<4>(acc, v0); vadd<4>(acc, v1); vadd<4>(acc, v2); vadd<4>(acc, v3);
+          }
+        }
+        for (; k < cnt; ++k) {
+          const int32_t c0 = __shfl_sync(0xffffffffu, my, k);
+          if (u_ok) vadd<4>(acc, __ldg(reinterpret_cast<const float4*>(x + (int64_t)c0 * ldx + (int64_t)u * 4)));
+        }
+      }
+      if (u_ok) *reinterpret_cast<float4*>(partial + (c * units + u) * 4) = acc;
+    }
+  }
+}
+
+// One warp per hub bucket: init + its chunk partials in chunk order, mean, store.
+__global__ void __launch_bounds__(256) spmm_heavy_finish_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ rows,
+                                                                const int32_t* __restrict__ chunk_ptr, int n_heavy, int mean,
+                                                                int units, const float* __restrict__ partial,
+                                                                const float* __restrict__ init, int64_t ldinit,
+                                                                float* __restrict__ out, int64_t ldout) {
+  const int lane = threadIdx.x & 31;
+  const int j = (int)((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5));
+  if (j >= n_heavy) return;
+  const int32_t row = __ldg(rows + j);
+  const int deg = __ldg(ptr + row + 1) - __ldg(ptr + row);
+  const int64_t c0 = __ldg(chunk_ptr + j), nc = (deg + kHeavyDeg - 1) / kHeavyDeg;
+  for (int u = lane; u < units; u += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (init != nullptr) acc = *reinterpret_cast<const float4*>(init + (int64_t)row * ldinit + (int64_t)u * 4);
+    for (int64_t c = c0; c < c0 + nc; ++c) vadd<4>(acc, *reinterpret_cast<const float4*>(partial + (c * units + u) * 4));
+    if (mean && deg > 1) vdiv<4>(acc, (float)deg);
+    *reinterpret_cast<float4*>(out + (int64_t)row * ldout + (int64_t)u * 4) = acc;
+  }
+}
+
+int launch_spmm_graph(const mpgnn_graph_impl* g, int64_t rel, int transpose, int mean, const float* x, int64_t ldx,
+                      int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
+  const int32_t* ptr = (transpose ? g->csc_ptr : g->csr_ptr) + rel * g->n;
+  const int32_t* idx = transpose ? g->csc_idx : g->csr_idx;
+  const HeavyRows& hv = g->heavy[transpose ? 1 : 0];
+  const int64_t h0 = hv.count > 0 ? hv.rel_ptr_host[rel] : 0, h1 = hv.count > 0 ? hv.rel_ptr_host[rel + 1] : 0;
+  const bool vec4 = feat % 4 == 0 && ldx % 4 == 0 && ldout % 4 == 0 && (init == nullptr || ldinit % 4 == 0) &&
+                    aligned_to(x, 16) && aligned_to(out, 16) && (init == nullptr || aligned_to(init, 16));
+  if (h1 == h0 || !vec4)      // no hub bucket in this relation (or a layout only the general kernel takes)
+    return launch_spmm_skip(ptr, idx, g->n, mean, x, ldx, feat, init, ldinit, out, ldout, 0, s);
+  MPGNN_PROPAGATE(launch_spmm_skip(ptr, idx, g->n, mean, x, ldx, feat, init, ldinit, out, ldout, kHeavyDeg, s));
+  const int n_heavy = (int)(h1 - h0);
+  const int64_t n_chunks = hv.rel_chunks_host[rel];
+  const int units = (int)(feat / 4);
+  float* partial = nullptr;
+  MPGNN_CUDA_CHECK(cudaMallocAsync(&partial, (size_t)n_chunks * feat * sizeof(float), s));   // stream ordered, hub relations only
+  int64_t blocks = ceil_div(n_chunks, 8);
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  spmm_heavy_chunk_kernel<<<(unsigned)blocks, 256, 0, s>>>(ptr, idx, hv.rows + h0, hv.chunk_ptr + h0, n_heavy, n_chunks, x, ldx,
+                                                           units, partial);
+  MPGNN_LAUNCH_CHECK();
+  spmm_heavy_finish_kernel<<<(unsigned)ceil_div(n_heavy, 8), 256, 0, s>>>(ptr, hv.rows + h0, hv.chunk_ptr + h0, n_heavy, mean, units,
+                                                                          partial, init, ldinit, out, ldout);
+  MPGNN_LAUNCH_CHECK();
+  MPGNN_CUDA_CHECK(cudaFreeAsync(partial, s));
+  return MPGNN_OK;
+}
+
+static int launch_spmm_skip(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
+                            int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, int skip_deg,
+                            cudaStream_t s) {
   if (n_rows <= 0 || feat <= 0) return MPGNN_OK;
   MPGNN_REQUIRE(feat <= (1 << 20), MPGNN_ENOTSUP, "spmm: feature width %lld too large", (long long)feat);
   const bool has_init = init != nullptr;
@@ -163,9 +275,9 @@ int launch_spmm(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean
     return feat % v == 0 && ldx % v == 0 && ldout % v == 0 && (!has_init || ldinit % v == 0) &&
            aligned_to(x, v * 4) && aligned_to(out, v * 4) && (!has_init || aligned_to(init, v * 4));
   };
-  if (ok(4)) return launch_vec<4>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, s);
-  if (ok(2)) return launch_vec<2>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, s);
-  return launch_vec<1>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, s);
+  if (ok(4)) return launch_vec<4>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, skip_deg, s);
+  if (ok(2)) return launch_vec<2>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, skip_deg, s);
+  return launch_vec<1>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, skip_deg, s);
 }
 
 }  // namespace mpgnn
