@@ -52,7 +52,6 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   float* bp = ws.take<float>(fwd_ws_floats(f_in, f_out));
   MPGNN_REQUIRE(bp != nullptr, MPGNN_EINVAL, "hop_fwd: workspace too small");
 
-  const int32_t* ptr = g->csr_ptr + rel * g->n;
   {
     ScopedTimer tm("spmm_mean_fwd", s);
     MPGNN_PROPAGATE(launch_spmm_graph(g, rel, /*transpose=*/0, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));

@@ -7,7 +7,7 @@
 // in TMEM as  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (the dropped lo*lo term is < 2^-24 relative),
 // which keeps the normalised error of the projection at the 1e-6 level (bar: 1e-5).
 //
-// Design (one persistent CTA per SM, no cluster):
+// Design (one persistent CTA per SM; an opt-in variant pairs CTAs with cta_group::2, see kPair below):
 //  * a CTA owns ONE column slice of BN outputs (BN*K*8 bytes of B, hi+lo, resident in shared
 //    memory for the whole kernel) and walks 128-row tiles; the CTAs owning the other slices of a
 //    row tile run next to it, so the second read of the A tile is an L2 hit.
@@ -19,10 +19,11 @@
 //    (a warp's wait -> LDS -> split -> tcgen05.st -> wait::st -> arrive chain is long, so consecutive
 //    chunks must not be serialised behind one warp) read their 32 rows x 16 K-columns conflict-free
 //    (the swizzle spreads the 8 rows of a quarter-warp over the 8 bank groups), split hi/lo in
-//    registers and tcgen05.st them into a 4-stage ring of TMEM columns (lane = row, column = k).
+//    registers and tcgen05.st them into a ring of TMEM column stages (lane = row, column = k): as many
+//    64-column stages as the two accumulators leave room for (six at BN = 64, four at BN = 128).
 //  * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8; 3 MMAs per K-step, A from
 //    TMEM) into one of two TMEM accumulators and tcgen05.commit's the barriers (the stage-free
-//    barrier once per pair of chunks: the serial issue path of this thread is what bounds the kernel).
+//    barrier once per pair of chunks: a commit holds the issuing thread for 130-240 cycles).
 //  * 8 epilogue warps (two per TMEM lane quarter, each owning alternate 32-column chunks)
 //    tcgen05.ld the accumulator and hand it back to the MMA warp at once, apply bias / degree
 //    normalisation / relu / dropout in registers (the kernel is specialised on the dropout mode
