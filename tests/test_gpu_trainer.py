@@ -91,3 +91,26 @@ def test_candidate_batch_runs_concurrently_and_matches_one_by_one(fx3):
     batch = mpgnn_b200.mpgnn_parallel_multiple_batch(data, 2, 64, 4, 64, 2, cands, epochs=40, seed=30, max_concurrent=4)
     assert batch == one_by_one
     assert len(set(batch)) > 1                      # different metapaths do train to different numbers
+
+
+def test_trainer_on_a_graph_with_hub_buckets_graph_replay_equals_eager(fx3):
+    """Hub buckets (> 256 edges) take the chunked aggregation path, which uses stream-ordered scratch: it has to
+    work inside the captured epoch graph exactly as in eager launches."""
+    ei, et = fx3["edge_index"].clone(), fx3["edge_type"].clone()
+    n = fx3["x"].size(0)
+    gen = torch.Generator().manual_seed(9)
+    hub_src = torch.randint(0, n, (700,), generator=gen)
+    ei = torch.cat([ei, torch.stack([torch.full((700,), 11), hub_src]), torch.stack([hub_src, torch.full((700,), 42)])], 1)
+    et = torch.cat([et, torch.full((700,), 1), torch.full((700,), 0)])      # hub target in relation 1, hub source in 0
+    data = mpgnn_b200.Data(x=fx3["x"], edge_index=ei, edge_type=et, num_nodes=n,
+                           **{k: fx3[k] for k in ("train_idx", "train_y", "val_idx", "val_y", "test_idx", "test_y")})
+    traces = {}
+    for use_graph in (True, False):
+        torch.manual_seed(30)
+        model = mpgnn_b200.MPNetm(2, 64, 4, 64, 2, 1, [[1, 0]], device="cpu")
+        tr = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, [1, 0], dropout_p=0.6, seed=5, max_epochs=12)
+        tr.load_state_dict(model.state_dict())
+        traces[use_graph] = tr.run(12, use_graph=use_graph)[:12]
+        assert np.all(np.isfinite(traces[use_graph]))
+    assert np.array_equal(traces[True], traces[False])
+    assert traces[True][-1, 0] < traces[True][0, 0]
