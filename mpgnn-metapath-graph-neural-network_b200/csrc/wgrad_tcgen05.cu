@@ -227,13 +227,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
           mbar_wait(bar_empty + 8 * s, sph ^ 1u);
 #ifndef MPGNN_WGRAD_EXP_NOFILL
           store(s, buf[j], mbuf[j]);
+          if (it + 2 < n_chunks) issue(buf[j], mbuf[j]);     // registers are free again: next loads go out before the fence
 #endif
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_full + 8 * s);
-#ifndef MPGNN_WGRAD_EXP_NOFILL
-          if (it + 2 < n_chunks) issue(buf[j], mbuf[j]);
-#endif
           if (++s == kStagesW) { s = 0; sph ^= 1u; }
         }
       }
