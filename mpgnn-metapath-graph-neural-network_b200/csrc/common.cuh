@@ -120,6 +120,9 @@ struct GemmRowsArgs {
   uint64_t seed; uint64_t offset; const uint8_t* mask_bits;
   const uint64_t* offset_ptr;             // optional device word added to `offset` (CUDA-graph replays)
   float* out; int64_t ldo;
+  // optional second destination: columns >= out_split go to out2[:, col - out_split] (0 = everything to `out`;
+  // the tcgen05 path needs a multiple of 32)
+  float* out2; int64_t ldo2; int64_t out_split;
   // activation bitmask (tcgen05 path only): word (row, c) bit j = [out(row, 32c+j) > 0]
   uint32_t* actmask_out;                  // written by the epilogue when non-null (needs n % 32 == 0)
   const uint32_t* a1_actmask; float a1_scale;   // A1(r,k) := bit(r,k) ? A1(r,k)*a1_scale : 0 (k2 must be 0)

@@ -45,7 +45,8 @@ __device__ __forceinline__ void gr_epilogue(const GemmRowsArgs& a, uint64_t laun
       const uint8_t byte = __ldg(a.mask_bits + row * mask_ld + (col >> 3));
       v = ((byte >> (7 - (col & 7))) & 1) ? v * scale : 0.f;
     }
-    a.out[row * a.ldo + col] = v;
+    if (a.out_split > 0 && col >= a.out_split) a.out2[row * a.ldo2 + (col - a.out_split)] = v;
+    else a.out[row * a.ldo + col] = v;
   }
 }
 

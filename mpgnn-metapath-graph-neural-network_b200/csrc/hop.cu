@@ -146,7 +146,9 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   }
 
   if (need_gx) {
-    // [t | g_z root^T] = g_z @ [W^T | root^T], first f_in columns divided by deg_r(row)
+    // [t | g_z root^T] = g_z @ [W^T | root^T], first f_in columns divided by deg_r(row).  The two halves go to two
+    // tensors: t to the workspace, g_z root^T straight into g_x, so that the transposed aggregation runs in place
+    // and touches only the rows of g_x that have incoming messages.
     MPGNN_PROPAGATE(launch_pack_b(bp2, 2 * f_in, w, 1, f_out, f_out, f_in, s));
     MPGNN_PROPAGATE(launch_pack_b(bp2 + f_in, 2 * f_in, root, 1, f_out, f_out, f_in, s));
     GemmRowsArgs a{};
@@ -154,7 +156,8 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
     a.a2 = nullptr; a.lda2 = 0; a.k2 = 0;
     a.b = bp2; a.m = n; a.n = 2 * f_in;
     a.deg_ptr = g->csr_ptr + rel * n; a.deg_cols = f_in;
-    a.out = t; a.ldo = 2 * f_in;
+    a.out = t; a.ldo = f_in;
+    a.out2 = gx; a.ldo2 = f_in; a.out_split = f_in;
     a.a1_actmask = fused_mask; a.a1_scale = scale;
     if (tc_d) {
       ScopedTimer tm("dgrad_nt_tcgen05", s);
@@ -163,9 +166,9 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
       ScopedTimer tm("dgrad_nt_simt", s);
       MPGNN_PROPAGATE(launch_gemm_rows(a, s));
     }
-    // g_x[j] = (g_z root^T)[j] + sum_{e: col(e)=j} t[row(e)]
+    // g_x[j] += sum_{e: col(e)=j} t[row(e)]
     ScopedTimer tm("spmm_transpose_bwd", s);
-    MPGNN_PROPAGATE(launch_spmm_graph(g, rel, /*transpose=*/1, /*mean=*/0, t, 2 * f_in, f_in, t + f_in, 2 * f_in, gx, f_in, s));
+    MPGNN_PROPAGATE(launch_spmm_graph(g, rel, /*transpose=*/1, /*mean=*/0, t, f_in, f_in, gx, f_in, gx, f_in, s));
   }
   return MPGNN_OK;
 }

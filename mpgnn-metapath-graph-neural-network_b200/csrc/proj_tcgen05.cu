@@ -71,6 +71,7 @@ struct Params {
   int dropout_mode; uint32_t dropout_thr16; float dropout_scale; uint64_t seed; uint64_t offset;
   const uint8_t* mask_bits; const uint64_t* offset_ptr;
   float* out; int64_t ldo;
+  int out_split;                               // columns >= out_split are stored through tmap_out2 (0 = off)
   uint32_t* actmask_out;                       // [m][n/32] words, bit j of word c = [out(row, 32c+j) > 0]
   int n_stages;   // TMEM A stages in use (even, <= kStages): 512 columns = acc_bufs * bn + 64 * n_stages
   int acc_bufs;   // TMEM accumulators: 2 (double buffered) or 1 (released right after the epilogue's tcgen05.ld)
@@ -122,7 +123,8 @@ __global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, 
 template <int kDrop, bool kDeg, bool kMasked, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_a1,
                                                                    const __grid_constant__ CUtensorMap tmap_a2,
-                                                                   const __grid_constant__ CUtensorMap tmap_out) {
+                                                                   const __grid_constant__ CUtensorMap tmap_out,
+                                                                   const __grid_constant__ CUtensorMap tmap_out2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int K = p.k1 + p.k2;
   const int BN = p.bn;                                    // accumulator width
@@ -386,9 +388,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         fence_proxy_async();
         __syncwarp();
         if (lane == 0 && !TC_EXP(16)) {
+          const bool second = p.out_split > 0 && col0 >= p.out_split;   // e.g. dgrad: [t | g_z root^T] to two tensors
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmap_out)),
-                       "r"(stg_tile), "r"(col0), "r"((int)(row0 + quarter * 32))
+                           reinterpret_cast<uint64_t>(second ? &tmap_out2 : &tmap_out)),
+                       "r"(stg_tile), "r"(second ? col0 - p.out_split : col0), "r"((int)(row0 + quarter * 32))
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -563,6 +566,9 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   MPGNN_REQUIRE(a.deg_ptr == nullptr || a.deg_cols % tc::kEpiCols == 0, MPGNN_ENOTSUP,
                 "proj_tcgen05: deg_cols must be a multiple of 32");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  MPGNN_REQUIRE(a.out_split == 0 || (a.out_split % tc::kEpiCols == 0 && a.out_split < a.n && a.out2 != nullptr &&
+                                     al16(a.out2) && a.ldo2 % 4 == 0),
+                MPGNN_EINVAL, "proj_tcgen05: out_split must be a multiple of 32 inside [0, n) with an aligned out2");
   MPGNN_REQUIRE(al16(a.a1) && (a.k2 == 0 || al16(a.a2)) && al16(a.out) && a.lda1 % 4 == 0 &&
                     (a.k2 == 0 || a.lda2 % 4 == 0) && a.ldo % 4 == 0,
                 MPGNN_EINVAL, "proj_tcgen05: operands must be 16-byte aligned with strides multiple of 4");
@@ -588,7 +594,7 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   p.deg_ptr = a.deg_ptr; p.deg_cols = a.deg_ptr ? (int)a.deg_cols : 0;
   p.dropout_mode = a.dropout_mode; p.dropout_thr16 = a.dropout_thr16; p.dropout_scale = a.dropout_scale;
   p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits; p.offset_ptr = a.offset_ptr;
-  p.out = a.out; p.ldo = a.ldo;
+  p.out = a.out; p.ldo = a.ldo; p.out_split = (int)a.out_split;
   p.actmask_out = a.actmask_out; p.a_actmask = a.a1_actmask; p.a_scale = a.a1_scale;
   // TMEM budget (512 columns): two accumulators + as many 64-column A stages as fit: six at BN = 64 (measured:
   // forward 3.81 -> 3.59 ms against four), four at BN = 128 (one accumulator + six stages was slower: 3.39 -> 3.85 ms)
@@ -607,11 +613,17 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   const size_t smem = (size_t)2 * k * bnb * 4 + (size_t)tc::kRawStages * tc::kRawBytes +
                       (size_t)tc::kEpiWarps * tc::kStgBytes + 128 * 4 +
                       (2 * tc::kStages + 4 + 2 * tc::kRawStages) * 8 + 16;
-  CUtensorMap map1, map2, map_out;
+  CUtensorMap map1, map2, map_out, map_out2;
   MPGNN_PROPAGATE(make_tensor_map(&map1, a.a1, a.m, a.k1, a.lda1, tc::kTileM));
   if (a.k2 > 0) MPGNN_PROPAGATE(make_tensor_map(&map2, a.a2, a.m, a.k2, a.lda2, tc::kTileM));
   else map2 = map1;
-  MPGNN_PROPAGATE(make_tensor_map(&map_out, a.out, a.m, a.n, a.ldo, 32));
+  if (a.out_split > 0) {
+    MPGNN_PROPAGATE(make_tensor_map(&map_out, a.out, a.m, a.out_split, a.ldo, 32));
+    MPGNN_PROPAGATE(make_tensor_map(&map_out2, a.out2, a.m, a.n - a.out_split, a.ldo2, 32));
+  } else {
+    MPGNN_PROPAGATE(make_tensor_map(&map_out, a.out, a.m, a.n, a.ldo, 32));
+    map_out2 = map_out;
+  }
   auto launch = [&](auto kernel) -> int {
     // the opt-in limit is per function and process wide: always raise it to the device maximum, so that concurrent
     // launches of the same kernel with different tile sizes (candidate trainers on several host threads) cannot
@@ -629,11 +641,11 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
       attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
       cfg.attrs = &attr;
       cfg.numAttrs = 1;
-      MPGNN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p, map1, map2, map_out));
+      MPGNN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p, map1, map2, map_out, map_out2));
       count_launch();
       return MPGNN_OK;
     }
-    kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p, map1, map2, map_out);
+    kernel<<<(unsigned)grid, tc::kThreads, smem, s>>>(p, map1, map2, map_out, map_out2);
     MPGNN_LAUNCH_CHECK();
     return MPGNN_OK;
   };

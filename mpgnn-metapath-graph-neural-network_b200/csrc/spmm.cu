@@ -121,6 +121,111 @@ __global__ void __launch_bounds__(256) spmm_gather_kernel(const int32_t* __restr
   }
 }
 
+// In-place accumulation, out[j,:] += sum over bucket j (the transposed aggregation of the backward: g_x already
+// holds g_z root^T).  A bucket without edges needs neither a read nor a write, and with E_r << N that is most rows
+// (73 % at C4), so this variant never touches them: lane l of a warp fetches the pointers of row base + l (one
+// coalesced load per 32 rows instead of a dependent broadcast load per row), a ballot marks the rows with edges,
+// and the warp then walks only those, kRowsInFlight per LPR-lane group at a time with their accumulator, index
+// and first-gather loads issued together.  Per row the sum starts from the stored value and adds the bucket in
+// edge order, exactly like the general kernel with init == out.
+template <int LPR>
+__global__ void __launch_bounds__(256) spmm_accumulate_kernel(const int32_t* __restrict__ ptr,
+                                                              const int32_t* __restrict__ idx, int64_t n_rows, int mean,
+                                                              const float* __restrict__ x, int64_t ldx, int units,
+                                                              float* out, int64_t ldout, int skip_deg) {
+  constexpr int G = 32 / LPR;            // rows a warp works on side by side
+  constexpr int J = 2;                   // rows in flight per group (kRowsInFlight)
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int grp = lane / LPR;
+  const unsigned grp_mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+
+  for (int64_t base = warp_id * 32; base < n_rows; base += n_warps * 32) {
+    const int64_t my_row = base + lane;
+    int32_t beg = 0, end = 0;
+    if (my_row < n_rows) {
+      beg = __ldg(ptr + my_row);
+      end = __ldg(ptr + my_row + 1);
+    }
+    const int my_deg = end - beg;
+    unsigned todo = __ballot_sync(0xffffffffu, my_deg > 0 && !(skip_deg > 0 && my_deg > skip_deg));
+    while (todo != 0u) {                 // warp uniform
+      int src[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) src[j] = -1;
+#pragma unroll
+      for (int t = 0; t < J * G; ++t) {  // hand the next J*G rows with edges to the groups
+        const int b = todo != 0u ? __ffs(todo) - 1 : -1;
+        todo &= todo - 1u;               // 0 stays 0
+        if (t % G == grp) src[t / G] = b;
+      }
+      int32_t rb[J], re[J];
+      int64_t row[J];
+      bool ok[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        ok[j] = src[j] >= 0;             // uniform inside the group
+        rb[j] = __shfl_sync(0xffffffffu, beg, src[j] & 31);
+        re[j] = __shfl_sync(0xffffffffu, end, src[j] & 31);
+        row[j] = base + (src[j] & 31);
+      }
+      for (int u0 = 0; u0 < units; u0 += LPR) {
+        const int u = u0 + sub;
+        const bool u_ok = u < units;
+        float4 acc[J], first[J];
+        int32_t my[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[j] && u_ok) acc[j] = *reinterpret_cast<const float4*>(out + row[j] * ldout + (int64_t)u * 4);
+          my[j] = (ok[j] && rb[j] + sub < re[j]) ? __ldg(idx + rb[j] + sub) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {    // every row's first gather in flight before the first add
+          const int32_t c = __shfl_sync(0xffffffffu, my[j], grp * LPR);
+          first[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[j] && u_ok) first[j] = __ldg(reinterpret_cast<const float4*>(x + (int64_t)c * ldx + (int64_t)u * 4));
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          if (!ok[j]) continue;
+          vadd<4>(acc[j], first[j]);
+          int k = 1;                     // edge 0 of the first batch is in
+          for (int32_t b = rb[j]; b < re[j]; b += LPR) {
+            const int32_t mine = (b == rb[j]) ? my[j] : ((b + sub < re[j]) ? __ldg(idx + b + sub) : 0);
+            const int cnt = min(LPR, re[j] - b);
+            for (; k < cnt; ++k) {
+              const int32_t c = __shfl_sync(grp_mask, mine, grp * LPR + k);
+              if (u_ok) vadd<4>(acc[j], __ldg(reinterpret_cast<const float4*>(x + (int64_t)c * ldx + (int64_t)u * 4)));
+            }
+            k = 0;
+          }
+          if (u_ok) {
+            const int deg = re[j] - rb[j];
+            if (mean && deg > 1) vdiv<4>(acc[j], (float)deg);
+            *reinterpret_cast<float4*>(out + row[j] * ldout + (int64_t)u * 4) = acc[j];
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int LPR>
+static int launch_accumulate(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
+                             int units, float* out, int64_t ldout, int skip_deg, cudaStream_t s) {
+  int64_t blocks = ceil_div(ceil_div(n_rows, 32), 8);      // 8 warps per block, 32 rows per warp and pass
+  const int64_t cap = (int64_t)kNumSMs * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks > kNumSMs) blocks = (blocks / kNumSMs) * kNumSMs;
+  if (blocks < 1) blocks = 1;
+  spmm_accumulate_kernel<LPR><<<(unsigned)blocks, 256, 0, s>>>(ptr, idx, n_rows, mean, x, ldx, units, out, ldout, skip_deg);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
 template <int VEC, int LPR>
 static int launch_one(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
                       int units, const float* init, int64_t ldinit, float* out, int64_t ldout, int skip_deg, cudaStream_t s) {
@@ -275,6 +380,12 @@ static int launch_spmm_skip(const int32_t* ptr, const int32_t* idx, int64_t n_ro
     return feat % v == 0 && ldx % v == 0 && ldout % v == 0 && (!has_init || ldinit % v == 0) &&
            aligned_to(x, v * 4) && aligned_to(out, v * 4) && (!has_init || aligned_to(init, v * 4));
   };
+  if (ok(4) && init == out && ldinit == ldout && feat >= 32) {   // in place: only rows with edges are touched
+    const int units = (int)(feat / 4);
+    if (units <= 8) return launch_accumulate<8>(ptr, idx, n_rows, mean, x, ldx, units, out, ldout, skip_deg, s);
+    if (units <= 16) return launch_accumulate<16>(ptr, idx, n_rows, mean, x, ldx, units, out, ldout, skip_deg, s);
+    return launch_accumulate<32>(ptr, idx, n_rows, mean, x, ldx, units, out, ldout, skip_deg, s);
+  }
   if (ok(4)) return launch_vec<4>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, skip_deg, s);
   if (ok(2)) return launch_vec<2>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, skip_deg, s);
   return launch_vec<1>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, skip_deg, s);

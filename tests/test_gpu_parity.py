@@ -135,6 +135,53 @@ def test_k2_spmm_hub_buckets_chunked_path(feat):
             assert torch.equal(out_sum, _spmm(g, rel, xd, transpose=transpose, mean=False))     # deterministic
 
 
+def _spmm_inplace(g, rel, x, buf, transpose=False, mean=False):
+    lib = _lib.load()
+    rc = lib.mpgnn_spmm(g.handle, rel, int(transpose), int(mean), _lib.ptr(x), x.stride(0), x.size(1),
+                        _lib.ptr(buf), buf.stride(0), _lib.ptr(buf), buf.stride(0), _lib.current_stream())
+    _lib.check(rc)
+    return buf
+
+
+@pytest.mark.parametrize("feat", [8, 32, 36, 64, 128, 256, 260])
+@pytest.mark.parametrize("shape", ["sparse", "dense", "hub"])
+def test_k2_spmm_in_place_equals_out_of_place(feat, shape):
+    """d_init aliasing d_out (the backward's g_x += A^T t): rows without edges are neither read nor written and the
+    others start from the stored value and add their bucket in edge order -- bit for bit the out-of-place result,
+    for the shapes that take the skipping kernel (feat % 4 == 0, >= 32) and those that do not."""
+    gen = torch.Generator().manual_seed(feat)
+    if shape == "sparse":          # most buckets empty, like one relation of C4; n not a multiple of 32
+        n, e, r = 50021, 30000, 3
+    elif shape == "dense":         # degrees around 40: several index batches per row at every group width
+        n, e, r = 1500, 120000, 2
+    else:
+        n, e, r = 6000, 60000, 3
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    et = torch.randint(0, r, (e,), generator=gen)
+    if shape == "hub":
+        ei[1, :9000] = 17          # hub source in the transposed view (36 chunks) ...
+        ei[0, 9000:9300] = 4000    # ... and a hub target in the forward view
+        et[:9300] = 1
+    g = mpgnn_b200.RelationGraph(ei, et, n, r, device=DEV)
+    x = torch.randn(n, feat, generator=gen).to(DEV)
+    init = torch.randn(n, feat, generator=gen).to(DEV)
+    for rel in range(r):
+        for transpose in (False, True):
+            for mean in (False, True):
+                ref = _spmm(g, rel, x, transpose=transpose, mean=mean, init=init)
+                got = _spmm_inplace(g, rel, x, init.clone(), transpose=transpose, mean=mean)
+                assert torch.equal(got, ref), (rel, transpose, mean)
+    # a strided destination (columns of a wider tensor) stays inside its columns
+    wide = torch.randn(n, 2 * feat + 4, generator=gen).to(DEV)
+    if (feat % 4) == 0:
+        keep = wide.clone()
+        view = wide[:, feat:2 * feat]
+        ref = _spmm(g, 1, x, transpose=True, mean=False, init=view)
+        _spmm_inplace(g, 1, x, view, transpose=True)
+        assert torch.equal(view, ref)
+        assert torch.equal(wide[:, :feat], keep[:, :feat]) and torch.equal(wide[:, 2 * feat:], keep[:, 2 * feat:])
+
+
 def test_k2_spmm_transpose_is_adjoint():
     n, e, r, f = 20000, 150000, 8, 64
     ei, et = _rand_graph(n, e, r, seed=3)
