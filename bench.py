@@ -111,17 +111,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def algorithmic_bytes(n, e_r, f):
-    """SURVEY.md section 8(d), fp32 values / int32 indices, gathers counted without reuse."""
+def algorithmic_bytes(n, e_r, f, rows_in=None):
+    """SURVEY.md section 8(d), fp32 values / int32 indices, gathers counted without reuse.  rows_in = rows of g_x
+    with incoming messages of the relation (the in-place transposed aggregation touches no others)."""
+    rows_in = n if rows_in is None else rows_in
     return {
         "spmm_mean_fwd": 4 * (e_r * (f + 1) + n * f + (n + 1)),
         "layer_fwd_fused": 4 * (n * (f + f) + e_r * (f + 1) + (n + 1)),
         "layer_bwd": 4 * (n * (2 * f + 2 * f) + e_r * (2 * f + 2) + 2 * (n + 1)),
-        "spmm_transpose_bwd": 4 * (e_r * (f + 1) + 2 * n * f + (n + 1)),
+        "spmm_transpose_bwd": 4 * (e_r * (f + 1) + 2 * rows_in * f + (n + 1)),     # g_x[row] += ..., rows with edges only
         # dense kernels of the hop as built here (h, t and the [y>0] bitmask are materialised; g_z is not):
         "proj_fwd": 4 * n * (2 * f + f) + n * f // 8,          # read h, x; write y (+ bitmask)
         "wgrad_tn": 4 * n * 3 * f + n * f // 8,                # read h, x, g_y (+ bitmask)
-        "dgrad_nt": 4 * n * (f + 2 * f) + n * f // 8,          # read g_y (+ bitmask); write t = [g_z W^T/deg | g_z root^T]
+        "dgrad_nt": 4 * n * (f + 2 * f) + n * f // 8,          # read g_y (+ bitmask); write t = g_z W^T/deg and g_z root^T (into g_x)
         "relu_dropout_bwd": 4 * n * 3 * f,
     }
 
@@ -159,6 +161,8 @@ def run_ours(args):
     graph = mpgnn_b200.RelationGraph(ei, et, n, r)
     torch.cuda.synchronize()
     build_s = time.time() - t0
+    # distinct (relation, message source) pairs = rows of g_x the transposed aggregation touches, mean per relation
+    rows_in_mean = int(torch.unique(et * n + ei[1]).numel()) // r
     del ei, et
     torch.cuda.empty_cache()
     x = torch.randn(n, f, device=dev, generator=gen)
@@ -302,7 +306,7 @@ def run_ours(args):
     if rank != 0:
         return
     hbm, tf, how = _peaks()
-    ab = algorithmic_bytes(n, e_r_mean, f)
+    ab = algorithmic_bytes(n, e_r_mean, f, rows_in_mean)
     per_kernel = {}
     total_ms = sum(v[0] for v in kern.values()) or 1.0
     for k, (kms, calls) in kern.items():

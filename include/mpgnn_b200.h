@@ -108,7 +108,9 @@ int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int6
  * accumulated.  d_gx may be NULL without MPGNN_F_NEED_GX.  [y>0] is taken from d_actmask
  * (the bitmask mpgnn_hop_fwd wrote) when it is non-NULL, else from d_y; one of the two is
  * required with MPGNN_F_RELU.  With the bitmask the tensor-core kernels gate g_y while
- * loading it and g_z is never written to memory. */
+ * loading it and g_z is never written to memory.  d_gx must not overlap d_gy or any other
+ * argument: the projection writes g_z root^T into it while g_y is still being read, and
+ * the transposed aggregation then adds in place, touching only rows with incoming edges. */
 int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, const float* d_h, const float* d_y,
                   const uint32_t* d_actmask, const float* d_gy, int64_t f_in, const float* d_w, const float* d_root,
                   int64_t f_out, uint32_t flags, double dropout_p, float* d_gx, float* d_gw, float* d_groot,

@@ -43,13 +43,15 @@ def _unpack_actmask(words, f_out):
     return ((words.to(torch.int64).unsqueeze(-1) >> sh) & 1).bool().reshape(words.size(0), f_out)
 
 
-def _bwd(graph, rel, x, h, y, gy, w, root, flags, actmask=None):
+def _bwd(graph, rel, x, h, y, gy, w, root, flags, actmask=None, ws_fill=None):
     lib = _lib.load()
     n, f_in = x.shape
     f_out = w.size(1)
     gx = torch.empty(n, f_in, device=DEV)
     gw, gr, gb = torch.empty_like(w), torch.empty_like(root), torch.empty(f_out, device=DEV)
     ws = torch.empty(lib.mpgnn_hop_workspace_bytes(n, f_in, f_out), dtype=torch.uint8, device=DEV)
+    if ws_fill is not None:
+        ws.fill_(ws_fill)
     _lib.check(lib.mpgnn_hop_bwd(graph.handle, rel, _lib.ptr(x), _lib.ptr(h), _lib.ptr(y), _lib.ptr(actmask), _lib.ptr(gy), f_in,
                                  _lib.ptr(w), _lib.ptr(root), f_out, flags | _lib.F_NEED_GX, 0.6, _lib.ptr(gx),
                                  _lib.ptr(gw), _lib.ptr(gr), _lib.ptr(gb), _lib.ptr(ws), ws.numel(),
@@ -115,6 +117,37 @@ def test_activation_bitmask_replaces_y_in_the_backward(n, f_in, f_out, tc):
     got = _bwd(graph, 1, x, h, None, gy, w, root, flags, actmask=am)
     for a, c in zip(got, ref):
         assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("tc", [True, False])
+@pytest.mark.parametrize("n,e,f_in,f_out", [(40000, 12000, 128, 128), (40000, 12000, 64, 128), (9000, 200000, 128, 64),
+                                            (12345, 4000, 96, 64)])
+def test_backward_never_reads_what_it_does_not_write(n, e, f_in, f_out, tc):
+    """The input-gradient projection writes its two halves to two tensors and the transposed aggregation accumulates
+    into g_x in place, skipping the rows without incoming edges: with the workspace poisoned by NaN patterns the
+    result must be bit for bit the one obtained on a zeroed workspace (sparse relation: most rows have no edge;
+    dense relation: almost every row has), i.e. nothing is read before the call itself wrote it."""
+    ei, et = _graph(n, e, 1, seed=n + e)
+    gen = torch.Generator().manual_seed(n)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 1, device=DEV)
+    x = torch.randn(n, f_in, generator=gen).to(DEV)
+    gy = torch.randn(n, f_out, generator=gen).to(DEV)
+    w = (torch.randn(f_in, f_out, generator=gen) * 0.1).to(DEV)
+    root = (torch.randn(f_in, f_out, generator=gen) * 0.1).to(DEV)
+    b = (torch.randn(f_out, generator=gen) * 0.1).to(DEV)
+    flags = _lib.F_RELU | _lib.F_DROPOUT_SEED | (_lib.F_TF32X3 if tc else 0)
+    am = torch.empty((n, f_out // 32), dtype=torch.int32, device=DEV)
+    h, y = _fwd(graph, 0, x, w, root, b, flags, None, actmask=am)
+    clean = _bwd(graph, 0, x, h, None, gy, w, root, flags, actmask=am, ws_fill=0)
+    dirty = _bwd(graph, 0, x, h, None, gy, w, root, flags, actmask=am, ws_fill=0xFF)
+    for a, c in zip(dirty, clean):
+        assert bool(torch.isfinite(a).all())
+        assert torch.equal(a, c)
+    # and the input gradient is the oracle's
+    gz = gy.cpu() * (y.cpu() > 0) * 2.5
+    _, hh, cnt = orc.conv_forward(x.cpu(), ei, et, 0, w.cpu(), root.cpu(), b.cpu())
+    gx_ref = orc.conv_backward(x.cpu(), ei, et, 0, w.cpu(), root.cpu(), hh, cnt, gz)[0]
+    assert rel_err(dirty[0], gx_ref) < TOL
 
 
 def test_hop_tf32x3_seeded_dropout_same_stream_as_fp32():
