@@ -6,6 +6,7 @@
 // the per-epoch cost becomes one graph launch instead of ~60 kernel launches + a host sync.
 // Everything that changes from epoch to epoch (Adam step, dropout offsets, trace slot) lives in
 // device words advanced by the first kernel of the graph.
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -105,6 +106,9 @@ struct Trainer {
   TrainerState* st;
   void* ws;
   int64_t ws_bytes;
+  void* slab;                // the one device allocation every buffer above is carved from
+  size_t slab_bytes;
+  int slab_device;
   cudaGraphExec_t exec;
   cudaStream_t own_stream;   // capture is not allowed on the legacy default stream
   double cap_lr, cap_b1, cap_b2, cap_eps, cap_wd;
@@ -118,24 +122,122 @@ static int64_t trainer_ws_bytes(const Trainer& t) {
   return (hop > tn ? hop : tn) + 1024 * 8;
 }
 
-template <typename T>
-static cudaError_t dev_alloc(T** p, int64_t count) {
-  return cudaMalloc(reinterpret_cast<void**>(p), (size_t)(count > 0 ? count : 1) * sizeof(T));
+// ---- trainer memory -------------------------------------------------------------------------------------------------
+// A candidate trainer needs ~(4 L + 8) N H floats in about forty buffers and lives for one candidate (0.7 s at the
+// configs[1] size).  Forty cudaMalloc + forty cudaFree per candidate cost up to a second of driver time (unmapping
+// half a gigabyte synchronises the device), more than the training itself, so every trainer takes ONE slab and
+// slabs are recycled through a small process-wide cache instead of going back to the driver.
+struct SlabCache {
+  struct Entry { void* p; size_t bytes; int device; };
+  std::mutex mu;
+  std::vector<Entry> free_list;
+  static constexpr size_t kMaxEntries = 16;
+  static constexpr size_t kMaxBytes = (size_t)48 << 30;      // of a 180 GB part
+  size_t cached_bytes = 0;
+
+  cudaError_t get(size_t bytes, int device, void** p, size_t* got) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int best = -1;
+      for (int i = 0; i < (int)free_list.size(); ++i) {
+        const Entry& e = free_list[i];
+        if (e.device == device && e.bytes >= bytes && e.bytes <= bytes + bytes / 2 &&
+            (best < 0 || e.bytes < free_list[best].bytes))
+          best = i;
+      }
+      if (best >= 0) {
+        *p = free_list[best].p; *got = free_list[best].bytes;
+        cached_bytes -= free_list[best].bytes;
+        free_list.erase(free_list.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t ce = cudaMalloc(p, bytes);
+    if (ce == cudaErrorMemoryAllocation) {       // give the cached slabs back and retry once
+      (void)cudaGetLastError();
+      release(device);
+      ce = cudaMalloc(p, bytes);
+    }
+    *got = bytes;
+    return ce;
+  }
+  void put(void* p, size_t bytes, int device) {
+    if (p == nullptr) return;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (free_list.size() < kMaxEntries && cached_bytes + bytes <= kMaxBytes) {
+        free_list.push_back({p, bytes, device});
+        cached_bytes += bytes;
+        return;
+      }
+    }
+    cudaFree(p);
+  }
+  void release(int device) {
+    std::vector<Entry> drop;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < free_list.size();) {
+        if (free_list[i].device == device) {
+          drop.push_back(free_list[i]);
+          cached_bytes -= free_list[i].bytes;
+          free_list.erase(free_list.begin() + i);
+        } else {
+          ++i;
+        }
+      }
+    }
+    for (const Entry& e : drop) cudaFree(e.p);
+  }
+};
+static SlabCache g_slabs;
+
+// Hands out 256-byte aligned pieces of a slab; with base == nullptr it only measures.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  void take(T** p, int64_t count) {
+    const size_t bytes = ((size_t)(count > 0 ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (base != nullptr) *p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+  }
+};
+
+static void trainer_layout(Trainer* t, Carver& c) {
+  const int64_t n = t->n, hidden = t->hidden, classes = t->classes, np = t->n_params;
+  c.take(&t->params, np); c.take(&t->grads, np); c.take(&t->adam_m, np); c.take(&t->adam_v, np);
+  for (int k = 0; k < t->n_layers; ++k) {
+    c.take(&t->h[k], n * (k == 0 ? t->f_in : hidden));
+    c.take(&t->y[k], n * hidden);
+    if (hidden % 32 == 0) c.take(&t->am[k], n * (hidden / 32));
+  }
+  c.take(&t->gxa, n * hidden); c.take(&t->gxb, n * hidden);
+  c.take(&t->a1, n * hidden); c.take(&t->lg, n * classes); c.take(&t->logp, n * classes);
+  c.take(&t->glg, n * classes); c.take(&t->gz1, n * hidden);
+  c.take(&t->packed, hidden * (hidden > classes ? hidden : classes));
+  c.take(&t->loss_train, 1); c.take(&t->loss_val, 1);
+  c.take(&t->f1_train, 1); c.take(&t->f1_val, 1); c.take(&t->trace, 4 * t->trace_capacity);
+  c.take(&t->cm, classes * classes); c.take(&t->st, 1);
+  char* ws = nullptr;
+  c.take(&ws, t->ws_bytes);
+  t->ws = ws;
 }
 
 void trainer_free(Trainer* t) {
   if (!t) return;
   if (t->exec) cudaGraphExecDestroy(t->exec);
   if (t->own_stream) cudaStreamDestroy(t->own_stream);
-  float* bufs[] = {t->params, t->grads, t->adam_m, t->adam_v, t->gxa, t->gxb, t->a1, t->lg, t->logp, t->glg,
-                   t->gz1, t->packed, t->loss_train, t->loss_val};
-  for (float* b : bufs) cudaFree(b);
-  for (int k = 0; k < 8; ++k) {
-    cudaFree(t->h[k]);
-    cudaFree(t->y[k]);
-    cudaFree(t->am[k]);
+  if (t->slab != nullptr) {
+    // the slab may be handed to the next trainer at once: everything queued on it must have finished (what the
+    // implicit synchronisation of cudaFree used to guarantee)
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != t->slab_device) cudaSetDevice(t->slab_device);
+    cudaDeviceSynchronize();
+    g_slabs.put(t->slab, t->slab_bytes, t->slab_device);
+    if (cur != t->slab_device) cudaSetDevice(cur);
   }
-  cudaFree(t->f1_train); cudaFree(t->f1_val); cudaFree(t->trace); cudaFree(t->cm); cudaFree(t->st); cudaFree(t->ws);
   delete t;
 }
 
@@ -170,30 +272,19 @@ int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int6
   t->off_b2 = off; off += classes;
   t->n_params = off;
   t->trace_capacity = max_epochs > 0 ? max_epochs : 1;
-  const int64_t n = t->n;
-  cudaError_t ce = cudaSuccess;
-#define TR_ALLOC(ptr, count) if (ce == cudaSuccess) ce = dev_alloc(&(ptr), (count))
-  TR_ALLOC(t->params, off); TR_ALLOC(t->grads, off); TR_ALLOC(t->adam_m, off); TR_ALLOC(t->adam_v, off);
-  for (int k = 0; k < n_layers; ++k) {
-    TR_ALLOC(t->h[k], n * (k == 0 ? f_in : hidden));
-    TR_ALLOC(t->y[k], n * hidden);
-    if (hidden % 32 == 0) TR_ALLOC(t->am[k], n * (hidden / 32));
-  }
-  TR_ALLOC(t->gxa, n * hidden); TR_ALLOC(t->gxb, n * hidden);
-  TR_ALLOC(t->a1, n * hidden); TR_ALLOC(t->lg, n * classes); TR_ALLOC(t->logp, n * classes);
-  TR_ALLOC(t->glg, n * classes); TR_ALLOC(t->gz1, n * hidden);
-  TR_ALLOC(t->packed, hidden * (hidden > classes ? hidden : classes));
-  TR_ALLOC(t->loss_train, 1); TR_ALLOC(t->loss_val, 1);
-  TR_ALLOC(t->f1_train, 1); TR_ALLOC(t->f1_val, 1); TR_ALLOC(t->trace, 4 * t->trace_capacity);
-  TR_ALLOC(t->cm, classes * classes); TR_ALLOC(t->st, 1);
   t->ws_bytes = trainer_ws_bytes(*t);
-  if (ce == cudaSuccess) ce = cudaMalloc(&t->ws, (size_t)t->ws_bytes);
-#undef TR_ALLOC
+  Carver measure{nullptr};
+  trainer_layout(t, measure);
+  cudaError_t ce = cudaGetDevice(&t->slab_device);
+  if (ce == cudaSuccess) ce = g_slabs.get(measure.off, t->slab_device, &t->slab, &t->slab_bytes);
   if (ce != cudaSuccess) {
-    set_error("trainer: allocation failed: %s", cudaGetErrorString(ce));
+    set_error("trainer: allocation of %zu bytes failed: %s", measure.off, cudaGetErrorString(ce));
+    t->slab = nullptr;
     trainer_free(t);
     return MPGNN_ECUDA;
   }
+  Carver carve{static_cast<char*>(t->slab)};
+  trainer_layout(t, carve);
   *out = t;
   return MPGNN_OK;
 }
