@@ -105,17 +105,24 @@ def create_bags(edg_dictionary, dest_dictionary, data):
     """main.py:545-572: per source, destinations whose every source label is > 0.9 form one positive
     bag; every other destination is a singleton negative bag; duplicate bags are dropped."""
     bag, labels, seen_single = [], [], set()
+    present = set()            # tuple(b) of every bag appended so far: the reference's `[value] not in bag` is a list
+    all_positive = {}          # scan per singleton, quadratic in the number of bags; min(labels) is taken once per node
     for key in edg_dictionary:
         lst = []
         for value in edg_dictionary[key]:
-            if min(dest_dictionary[value]) > 0.9:
+            pos = all_positive.get(value)
+            if pos is None:
+                pos = all_positive[value] = min(dest_dictionary[value]) > 0.9
+            if pos:
                 lst.append(value)
             elif value not in seen_single:
                 seen_single.add(value)
-                if [value] not in bag:
+                if (value,) not in present:
+                    present.add((value,))
                     bag.append([value])
                     labels.append(0)
         if lst:
+            present.add(tuple(lst))
             bag.append(lst)
             labels.append(1)
     new_bag, new_labels, seen = [], [], set()
@@ -373,10 +380,16 @@ def clean_dictionaries(data, edg_dict, dest_dict, mod):
     """main.py:456-477: drop sources whose feature . LinearLayerAttri weight is < 0.01 (and one 0
     label from each of their destinations)."""
     edge_copy, dest_copy = edg_dict.copy(), dest_dict.copy()
-    lin = mod.output.LinearLayerAttri.weight[0]
-    x = data.x.to(torch.float32)
-    for key in edg_dict:
-        if torch.dot(x[key].cpu(), lin.cpu()).item() < 0.01:
+    lin = mod.output.LinearLayerAttri.weight[0].detach().cpu()
+    x = data.x.to(torch.float32).cpu()
+    keys = list(edg_dict)
+    # one batched product instead of a tensor op per source; a value within 1e-6 of the threshold is re-evaluated
+    # with the reference's own torch.dot, so the decision is the reference's bit for bit
+    approx = (x[torch.as_tensor(keys, dtype=torch.long)] * lin).sum(dim=1).tolist() if keys else []
+    for key, a in zip(keys, approx):
+        if abs(a - 0.01) < 1e-6:
+            a = torch.dot(x[key], lin).item()
+        if a < 0.01:
             for destination in edge_copy[key]:
                 if 0 in dest_copy[destination]:
                     dest_copy[destination].remove(0)
