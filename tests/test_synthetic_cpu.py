@@ -51,6 +51,31 @@ def test_files_are_byte_identical(name, tmp_path):
         assert open(os.path.join(str(tmp_path), fname)).read() == str(g["file_" + fname]), fname
 
 
+def test_both_tsv_writers_give_the_same_bytes(tmp_path, monkeypatch):
+    """pyarrow's CSV writer (fast path) and the numpy.savetxt fallback, including the trailing tab of embedding.dat."""
+    import builtins
+    g = _case(CASES[0])
+    table = np.hstack([np.arange(len(g["embedding"]))[:, None], g["embedding"]])
+    fast, slow = str(tmp_path / "fast.dat"), str(tmp_path / "slow.dat")
+    syn._write_tsv(fast, table, trailing_tab=True)
+    real_import = builtins.__import__
+
+    def no_pyarrow(name, *a, **k):
+        if name.startswith("pyarrow"):
+            raise ImportError(name)
+        return real_import(name, *a, **k)
+
+    monkeypatch.setattr(builtins, "__import__", no_pyarrow)
+    syn._write_tsv(slow, table, trailing_tab=True)
+    monkeypatch.undo()
+    assert open(fast).read() == open(slow).read() == str(g["file_embedding.dat"])
+    syn._write_tsv(fast, g["post"])
+    monkeypatch.setattr(builtins, "__import__", no_pyarrow)
+    syn._write_tsv(slow, g["post"])
+    monkeypatch.undo()
+    assert open(fast).read() == open(slow).read() == str(g["file_link.dat"])
+
+
 def test_presets_cover_the_relations_the_reference_drew():
     """Every (colour pair, relation) the reference emitted is in the preset of that pair, and the planted relations are
     in the presets of their hops."""
