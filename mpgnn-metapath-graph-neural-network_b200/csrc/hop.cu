@@ -30,7 +30,7 @@ int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
   floats += align_up(wgrad_ws_floats(n, f_in, f_out), 64);             // split-K partials (SIMT or tcgen05)
   floats += align_up(f_out * 2 * f_in, 64);                            // packed [W^T | root^T]
   floats += align_up(proj_tcgen05_workspace_floats(f_out, 2 * f_in), 64);  // its hi/lo UMMA images
-  floats += align_up(n * 2 * f_in, 64);                                // [t | g_z root^T]
+  floats += align_up(n * f_in, 64);                                    // t = g_z W^T / deg (g_z root^T goes straight to g_x)
   return floats * 4 + 8 * 256;
 }
 
@@ -107,7 +107,7 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   float* partials = ws.take<float>(align_up(wgrad_ws_floats(n, f_in, f_out), 64));
   float* bp2 = ws.take<float>(align_up(f_out * 2 * f_in, 64));
   float* bp2_img = ws.take<float>(align_up(proj_tcgen05_workspace_floats(f_out, 2 * f_in), 64));
-  float* t = need_gx ? ws.take<float>(align_up(n * 2 * f_in, 64)) : nullptr;
+  float* t = need_gx ? ws.take<float>(align_up(n * f_in, 64)) : nullptr;
   MPGNN_REQUIRE(gz && partials && bp2 && bp2_img && (!need_gx || t), MPGNN_EINVAL, "hop_bwd: workspace too small");
 
   // g_z = g_y * [y > 0] * 1/(1-p).  With the activation bitmask and both tensor-core kernels available
