@@ -79,7 +79,9 @@ int mpgnn_graph_relation_counts(const mpgnn_graph* g, int64_t* h_counts);
  * mp_rgcn_layer.py:236: h[i,:] = sum_{e in E_r,row(e)=i} x[col(e),:] / max(1,deg_r(i)),
  * fp32 sum in edge order.  transpose=1 gives the backward's un-normalised transpose
  * gather  out[j,:] = init[j,:] + sum_{e in E_r,col(e)=j} x[row(e),:].  x/out row strides
- * in floats; d_init may be NULL (zeros) or alias d_out. */
+ * in floats; d_init may be NULL (zeros) or alias d_out.  With d_init == d_out (same stride)
+ * the call accumulates in place and neither reads nor writes the rows that have no edge of
+ * the relation -- the result is bit for bit the out-of-place one. */
 int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, const float* d_x, int64_t ldx,
                int64_t feat, const float* d_init, int64_t ldinit, float* d_out, int64_t ldout, void* stream);
 
