@@ -152,17 +152,30 @@ def reinitialize_weights(data, destination_dictionary, previous_weights, frozen,
     """main.py:499-516: frozen destinations keep their value, the others are re-drawn U(0,1)."""
     weights = torch.zeros(int(data.num_nodes))
     fz = set(frozen)
-    prev = previous_weights.reshape(-1)
-    for key in destination_dictionary:
-        weights[key] = prev[key] if key in fz else random.uniform(0.0, 1.0)
+    prev = previous_weights.reshape(-1).to(torch.float32).cpu()
+    keys = list(destination_dictionary)
+    if not keys:
+        return weights
+    # draws in dictionary order as in the reference, one scatter instead of a tensor write per destination
+    drawn = [0.0 if key in fz else random.uniform(0.0, 1.0) for key in keys]
+    idx = torch.as_tensor(keys, dtype=torch.long)
+    vals = torch.tensor(drawn, dtype=torch.float64).to(torch.float32)
+    keep = torch.tensor([key in fz for key in keys], dtype=torch.bool)
+    vals[keep] = prev[idx[keep]]
+    weights[idx] = vals
     return weights
 
 
 def initialize_weights(data, destination_dictionary, BAGS):
     """main.py:479-497: w[dst] = |min(source labels) + U(-0.2, 0.2)| in dict order (Python `random`)."""
     weights = torch.zeros(int(data.num_nodes))
-    for key, values in destination_dictionary.items():
-        weights[key] = abs(min(values) + random.uniform(-0.2, 0.2))
+    keys = list(destination_dictionary)
+    if not keys:
+        return weights
+    # same draws in the same order; one scatter instead of a tensor write per destination (double -> float32 rounding
+    # is the one the per-element assignment performs)
+    vals = [abs(min(values) + random.uniform(-0.2, 0.2)) for values in destination_dictionary.values()]
+    weights[torch.as_tensor(keys, dtype=torch.long)] = torch.tensor(vals, dtype=torch.float64).to(torch.float32)
     return weights
 
 
