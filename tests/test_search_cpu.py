@@ -249,3 +249,30 @@ def test_clean_dictionaries_matches_per_source_dot():
             del exp_e[key]
     assert e2 == exp_e and d2 == exp_d and list(e2) == list(exp_e)
     assert 0 < len(e2) < len(ed)
+
+
+def test_weight_initialisation_equals_the_per_destination_loop():
+    """initialize_weights / reinitialize_weights write all destinations with one scatter; the draws (Python `random`,
+    dictionary order) and the double -> float32 rounding are those of the reference's per-destination assignment
+    (main.py:479-516)."""
+    rng = np.random.default_rng(0)
+    n = 5000
+    dd = {int(k): [float(v) for v in rng.integers(0, 2, size=int(rng.integers(1, 4)))] for k in rng.permutation(n)[:1500]}
+    data = types.SimpleNamespace(num_nodes=n)
+    random.seed(5)
+    got = search.initialize_weights(data, dd, False)
+    random.seed(5)
+    exp = torch.zeros(n)
+    for key, values in dd.items():
+        exp[key] = abs(min(values) + random.uniform(-0.2, 0.2))
+    assert torch.equal(got, exp)
+    frozen = list(dd)[::3]
+    random.seed(6)
+    got2 = search.reinitialize_weights(data, dd, got.reshape(-1, 1), frozen)
+    random.seed(6)
+    exp2, fz = torch.zeros(n), set(frozen)
+    for key in dd:
+        exp2[key] = got[key] if key in fz else random.uniform(0.0, 1.0)
+    assert torch.equal(got2, exp2)
+    assert torch.equal(search.initialize_weights(data, {}, False), torch.zeros(n))
+    assert torch.equal(search.reinitialize_weights(data, {}, got, []), torch.zeros(n))
