@@ -54,11 +54,9 @@ def node_types_and_connected_relations(data_obj, BAGS, dataset):
     return [int(v) for v in pos[np.sort(first)]]
 
 
-def create_edge_dictionary(data, relation, source_nodes_mask, BAGS, dataset):
-    """main.py:387-438: ({src: [dst...]}, {dst: [label of each source...]}); in bag mode the second
-    dictionary lists, per destination, the labels of all bags that contain each of its sources."""
-    if BAGS:
-        return _bag_dictionaries(data, relation, source_nodes_mask)
+def _relation_edges(data, relation, source_nodes_mask, dataset):
+    """Edges of `relation` whose source is in the mask, in edge order, with the label of each source
+    (main.py:387-438 without the dictionaries): (mask list, sources, destinations, source labels)."""
     ei = _np(data.edge_index)
     sel = _np(data.edge_type) == int(relation)
     rows, cols = ei[0][sel], ei[1][sel]
@@ -71,6 +69,15 @@ def create_edge_dictionary(data, relation, source_nodes_mask, BAGS, dataset):
     else:                                                              # labels aligned with the mask list (:424)
         pos = {s: i for i, s in reversed(list(enumerate(mask_list)))}
         src_lab = lab[np.asarray([pos[int(s)] for s in rows], dtype=np.int64)] if len(rows) else lab[:0]
+    return mask_list, rows, cols, src_lab
+
+
+def create_edge_dictionary(data, relation, source_nodes_mask, BAGS, dataset):
+    """main.py:387-438: ({src: [dst...]}, {dst: [label of each source...]}); in bag mode the second
+    dictionary lists, per destination, the labels of all bags that contain each of its sources."""
+    if BAGS:
+        return _bag_dictionaries(data, relation, source_nodes_mask)
+    mask_list, rows, cols, src_lab = _relation_edges(data, relation, source_nodes_mask, dataset)
     present = set(rows.tolist())
     edge_dictionary = {s: [] for s in mask_list if s in present}
     destination_dictionary = {}
@@ -78,6 +85,23 @@ def create_edge_dictionary(data, relation, source_nodes_mask, BAGS, dataset):
         edge_dictionary[s].append(d)
         destination_dictionary.setdefault(d, []).append(l)
     return edge_dictionary, destination_dictionary
+
+
+def initial_weights_from_edges(num_nodes, cols, src_lab):
+    """`initialize_weights(create_edge_dictionary(...)[1])` without the dictionaries: destinations in first-appearance
+    order (the dictionary's key order, i.e. the order of the `random.uniform` draws), the minimum source label of each
+    by a scatter-min, w[dst] = |min + U(-0.2, 0.2)| formed in double and rounded to float32 once -- bit for bit the
+    dictionary path (tested)."""
+    weights = np.zeros(int(num_nodes), dtype=np.float32)
+    if len(cols) == 0:
+        return torch.from_numpy(weights)
+    uniq, first, inverse = np.unique(cols, return_index=True, return_inverse=True)
+    mins = np.full(len(uniq), np.inf, dtype=np.float64)
+    np.minimum.at(mins, inverse, np.asarray(src_lab, dtype=np.float64))
+    order = np.argsort(first, kind="stable")                  # first appearance in edge order
+    draws = np.array([random.uniform(-0.2, 0.2) for _ in range(len(uniq))], dtype=np.float64)
+    weights[uniq[order]] = np.abs(mins[order] + draws).astype(np.float32)
+    return torch.from_numpy(weights)
 
 
 def _bag_dictionaries(data, relation, source_nodes_mask):
@@ -208,18 +232,26 @@ def run_scorer(graph, relation, weights, node_labels, source_mask=None, epochs=S
     return traj.cpu(), w, arg
 
 
-def score_relation_parallel(data, relation, source_nodes, features_dim, dataset, device=None):
-    """main.py:727-760 -> (relation, final loss, edge_dictionary, destination_dictionary)."""
+def score_relation_parallel(data, relation, source_nodes, features_dim, dataset, device=None, dictionaries=True):
+    """main.py:727-760 -> (relation, final loss, edge_dictionary, destination_dictionary).
+    `dictionaries=False` returns (relation, final loss, None, None): the same loss (same initial weights, bit for
+    bit) without building the two Python dictionaries, which at the configs[4] size cost ~100x the device time of a
+    relation; `greedy_search` scores every relation this way and builds the dictionaries of the kept ones only."""
     relation = int(relation)
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     first = not source_nodes
     ei = _np(data.edge_index)
     if first:                                                          # main.py:733-735
         source_nodes = np.unique(ei[0][_np(data.edge_type) == relation]).tolist()
-    edge_dictionary, destination_dictionary = create_edge_dictionary(data, relation, source_nodes, BAGS=False,
-                                                                     dataset=dataset)
     random.seed(SCORER_SEED_BASE + relation)
-    weights = initialize_weights(data, destination_dictionary, BAGS=False)
+    if dictionaries:
+        edge_dictionary, destination_dictionary = create_edge_dictionary(data, relation, source_nodes, BAGS=False,
+                                                                         dataset=dataset)
+        weights = initialize_weights(data, destination_dictionary, BAGS=False)
+    else:
+        edge_dictionary = destination_dictionary = None
+        _, _, cols, src_lab = _relation_edges(data, relation, source_nodes, dataset)
+        weights = initial_weights_from_edges(data.num_nodes, cols, src_lab)
     n = int(data.num_nodes)
     lab = _np(data.labels).reshape(-1)
     if dataset == "synthetic":
@@ -519,10 +551,14 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381)."""
     from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_x, mpgnn_parallel_multiple_batch
     comm = comm or Comm()
+    dict_fn = None
     if score_fn is None:
-        def score_fn(d, rel):
-            r = score_relation_parallel(d, rel, d.source_nodes_mask, input_dim, dataset)
-            return r[1], r[2], r[3]
+        def score_fn(d, rel):            # the loss only: no dictionaries for relations the gap rule will drop
+            return score_relation_parallel(d, rel, d.source_nodes_mask, input_dim, dataset, dictionaries=False)[1]
+
+        def dict_fn(d, rel):             # what score_relation_parallel returns next to the loss (main.py:733-737)
+            sources = list(d.source_nodes_mask) or np.unique(_np(d.edge_index)[0][_np(d.edge_type) == int(rel)]).tolist()
+            return create_edge_dictionary(d, rel, sources, BAGS=False, dataset=dataset)
     if bag_score_fn is None:
         def bag_score_fn(bag_data, rel, mlen):
             return score_relation_bags_parallel(bag_data, rel, input_dim, dataset, metapath_len=mlen)
@@ -565,7 +601,9 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
         state = {}
         for rel in best:
             out = local_out.get(rel)
-            if not isinstance(out, tuple):                       # scored on another rank: recompute locally
+            if not isinstance(out, tuple) and dict_fn is not None:
+                out = (out,) + tuple(dict_fn(data, rel))         # dictionaries of the kept relations only
+            elif not isinstance(out, tuple):                     # scored on another rank: recompute locally
                 out = score_fn(data, rel)                        # (deterministic under the per-relation seed)
             if not isinstance(out, tuple):
                 state = None                                     # stand-in scorer without dictionaries: no bag steps

@@ -276,3 +276,97 @@ def test_weight_initialisation_equals_the_per_destination_loop():
     assert torch.equal(got2, exp2)
     assert torch.equal(search.initialize_weights(data, {}, False), torch.zeros(n))
     assert torch.equal(search.reinitialize_weights(data, {}, got, []), torch.zeros(n))
+
+
+def _record_scorer(monkeypatch):
+    """Replace the device scorer by a recorder: what reaches the GPU is the whole contract of the host side."""
+    calls = []
+
+    def fake_run_scorer(graph, relation, weights, node_labels, source_mask=None, epochs=None, lr=None):
+        calls.append((int(relation), weights.clone(), node_labels.clone(), None if source_mask is None else source_mask.clone()))
+        # deterministic, relation dependent; relations >= 2 sit above a gap the step-0 rule cuts at
+        loss = float(weights.double().sum() % 1.0) * 0.001 + 0.01 * int(relation) + (0.5 if int(relation) >= 2 else 0.0)
+        return torch.tensor([loss]), weights, None
+
+    monkeypatch.setattr(search, "run_scorer", fake_run_scorer)
+    monkeypatch.setattr(search, "_graph_of", lambda data, device: None)
+    return calls
+
+
+@pytest.mark.parametrize("dataset", ["synthetic", "fb15k-237"])
+def test_dictionary_free_scoring_hands_the_device_the_same_inputs(fx3, monkeypatch, dataset):
+    """score_relation_parallel(dictionaries=False) -- the form greedy_search uses for every relation -- must reach the
+    device scorer with bit-identical initial weights, labels and source mask as the dictionary-building form."""
+    calls = _record_scorer(monkeypatch)
+    data = _data(fx3)
+    n = fx3["x"].size(0)
+    if dataset == "synthetic":
+        masks = [[], np.unique(fx3["edge_index"].numpy()[0])[::2].tolist()]
+    else:                                            # labels aligned with the labelled-source list (main.py:424)
+        labelled = torch.randperm(n, generator=torch.Generator().manual_seed(1))[: n // 3].tolist()
+        data.labels = torch.randint(0, 2, (len(labelled), 1), generator=torch.Generator().manual_seed(2)).float()
+        masks = [labelled]
+    for mask in masks:
+        for rel in range(fx3["num_relations"]):
+            del calls[:]
+            full = search.score_relation_parallel(data, rel, list(mask), 2, dataset, device="cpu")
+            fast = search.score_relation_parallel(data, rel, list(mask), 2, dataset, device="cpu", dictionaries=False)
+            assert full[:2] == fast[:2] and fast[2] is None and fast[3] is None and isinstance(full[2], dict)
+            (r1, w1, l1, m1), (r2, w2, l2, m2) = calls
+            assert r1 == r2 == rel and torch.equal(w1, w2) and torch.equal(l1, l2)
+            assert (m1 is None and m2 is None) or torch.equal(m1, m2)
+            assert float(w1.abs().sum()) > 0
+    # the scatter-min form on its own, against the dictionary form, with repeated destinations and integer labels
+    rng = np.random.default_rng(0)
+    cols = rng.integers(0, 50, size=400)
+    lab = rng.integers(0, 2, size=400)
+    dd = {}
+    for d, l in zip(cols.tolist(), lab.tolist()):
+        dd.setdefault(d, []).append(l)
+    random.seed(9)
+    exp = search.initialize_weights(types.SimpleNamespace(num_nodes=60), dd, False)
+    random.seed(9)
+    assert torch.equal(search.initial_weights_from_edges(60, cols, lab), exp)
+    assert torch.equal(search.initial_weights_from_edges(60, cols[:0], lab[:0]), torch.zeros(60))
+
+
+def test_greedy_search_builds_dictionaries_for_kept_relations_only(fx3, monkeypatch):
+    """Default step 0 of greedy_search: every relation is scored without dictionaries, the kept ones get theirs from
+    create_edge_dictionary -- the same state, bags and candidates as when every score call returns its dictionaries."""
+    _record_scorer(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)      # the default score_fn names the current GPU
+    built = []
+    real_ced = search.create_edge_dictionary
+
+    def counting_ced(data, relation, mask, BAGS, dataset):
+        built.append(int(relation))
+        return real_ced(data, relation, mask, BAGS, dataset)
+
+    monkeypatch.setattr(search, "create_edge_dictionary", counting_ced)
+    seen_bags = []
+
+    def bag_score_fn(bag_data, rel, mlen):          # record the bags the state produced, then skip the relation
+        seen_bags.append((rel, mlen, [list(b) for b in bag_data.bags], bag_data.bag_labels.reshape(-1).tolist()))
+        return rel, 1.0, None, {}, True
+
+    def run(score_fn):
+        del seen_bags[:]
+        data = _data(fx3)
+        data.labels = torch.ones_like(data.labels)            # every relation is a candidate of step 0
+        res = search.greedy_search(data, None, 2, 64, fx3["num_relations"], 64, 2, "synthetic", score_fn=score_fn,
+                                   eval_fn=lambda meta: 0.5 + 0.01 * sum(meta), union_fn=lambda metas: 0.9,
+                                   bag_score_fn=bag_score_fn, max_depth=1)
+        return res, [tuple(map(str, b)) for b in seen_bags]
+
+    res_fast, bags_fast = run(None)
+    kept = res_fast["kept"]
+    assert sorted(set(built)) == sorted(kept) and len(kept) < len(res_fast["relations"])    # dictionaries: kept relations only
+
+    def tuple_score_fn(d, rel):
+        r = search.score_relation_parallel(d, rel, d.source_nodes_mask, 2, "synthetic", device="cpu")
+        return r[1], r[2], r[3]
+
+    res_full, bags_full = run(tuple_score_fn)
+    for key in ("relations", "losses", "kept", "candidates", "final_dict", "final_meta"):
+        assert res_fast[key] == res_full[key], key
+    assert bags_fast == bags_full and len(bags_fast) > 0
