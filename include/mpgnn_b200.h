@@ -33,7 +33,7 @@ extern "C" {
 #define MPGNN_F_DROPOUT_MASK 4u /* keep-mask supplied bit-packed, np.packbits(axis=1) layout */
 #define MPGNN_F_NEED_GX 8u      /* bwd: also produce the input gradient (hidden layers)      */
 #define MPGNN_F_TF32X3 16u      /* projection on tcgen05 with the 3xTF32 split (fp32 parity) */
-#define MPGNN_F_BF16 32u        /* projection on tcgen05 in bf16 (stated tolerance)          */
+#define MPGNN_F_BF16 32u        /* reserved: not built, every entry point rejects it (ENOTSUP) */
 
 typedef struct mpgnn_graph mpgnn_graph; /* relation-typed CSR + CSC, device resident */
 

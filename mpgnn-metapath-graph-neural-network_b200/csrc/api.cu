@@ -2,6 +2,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -30,9 +31,16 @@ static long long g_slot_calls[kMaxTimerSlots];
 static cudaEvent_t g_ev_start[kMaxTimerEvents], g_ev_stop[kMaxTimerEvents];
 static int g_ev_slot[kMaxTimerEvents];
 static int g_n_events = 0, g_n_events_created = 0;
+static std::mutex g_timer_mu;   // candidate trainers record from several host threads
 
 ScopedTimer::ScopedTimer(const char* name, cudaStream_t s) : slot(-1), stream(s) {
-  if (!g_timing || g_n_events >= kMaxTimerEvents) return;
+  if (!g_timing) return;
+  // events recorded while a stream is being captured belong to the graph and cannot be queried: no timing there
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  if (cap != cudaStreamCaptureStatusNone) return;
+  std::lock_guard<std::mutex> lk(g_timer_mu);
+  if (g_n_events >= kMaxTimerEvents) return;
   int k = 0;
   for (; k < g_n_slots; ++k)
     if (strncmp(g_slot_names[k], name, 47) == 0) break;
@@ -59,6 +67,7 @@ ScopedTimer::~ScopedTimer() {
 }
 
 static void timing_flush() {
+  std::lock_guard<std::mutex> lk(g_timer_mu);
   for (int i = 0; i < g_n_events; ++i) {
     float ms = 0.f;
     if (cudaEventSynchronize(g_ev_stop[i]) == cudaSuccess &&
@@ -68,6 +77,7 @@ static void timing_flush() {
     }
   }
   g_n_events = 0;
+  (void)cudaGetLastError();   // a failed query must not surface as the next launch's error
 }
 
 int graph_build_device(const int64_t* d_edge_index, const int64_t* d_edge_type, int64_t e, int64_t n, int64_t r,

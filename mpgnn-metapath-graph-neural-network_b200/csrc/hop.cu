@@ -46,6 +46,11 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   MPGNN_REQUIRE(!(drop_seed && drop_mask), MPGNN_EINVAL, "hop_fwd: both dropout modes set");
   MPGNN_REQUIRE(!(drop_seed || drop_mask) || (p >= 0.0 && p < 1.0), MPGNN_EINVAL, "hop_fwd: dropout p=%g", p);
   MPGNN_REQUIRE(!drop_mask || mask_bits, MPGNN_EINVAL, "hop_fwd: mask mode without mask");
+  MPGNN_REQUIRE(!(flags & MPGNN_F_BF16), MPGNN_ENOTSUP, "hop_fwd: MPGNN_F_BF16 is not built; use MPGNN_F_TF32X3");
+  // the backward recovers the dropped elements from [y > 0] (a dropped element is 0, a kept one relu(z)/(1-p)); without
+  // the relu y == 0 says nothing about the keep-mask, so that combination is refused instead of differentiated wrongly
+  MPGNN_REQUIRE(!(drop_seed || drop_mask) || (flags & MPGNN_F_RELU), MPGNN_ENOTSUP,
+                "hop_fwd: dropout without MPGNN_F_RELU is not built (model.py:210-214 always applies relu first)");
   MPGNN_REQUIRE(actmask == nullptr || f_out % 32 == 0, MPGNN_ENOTSUP,
                 "hop_fwd: the activation bitmask needs f_out %% 32 == 0 (got %lld)", (long long)f_out);
   Workspace ws(ws_ptr, ws_bytes);
@@ -70,7 +75,7 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   a.dropout_thr16 = dropout_threshold16(p); a.seed = seed; a.offset = offset; a.mask_bits = mask_bits;
   a.offset_ptr = offset_ptr;
   a.out = y; a.ldo = f_out;
-  if ((flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
+  if ((flags & MPGNN_F_TF32X3) && proj_tcgen05_supported(a.m, a.k1, a.k2, a.n, flags)) {
     ScopedTimer tm("proj_fwd_tcgen05", s);
     a.actmask_out = actmask;                           // written by the epilogue, no extra pass
     return launch_proj_tcgen05_ws(a, flags, bp + align_up(2 * f_in * f_out, 64), s);
@@ -99,6 +104,9 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   const bool need_gx = flags & MPGNN_F_NEED_GX;
   MPGNN_REQUIRE(!need_gx || gx, MPGNN_EINVAL, "hop_bwd: NEED_GX without d_gx");
   const bool drop = flags & (MPGNN_F_DROPOUT_SEED | MPGNN_F_DROPOUT_MASK);
+  MPGNN_REQUIRE(!(flags & MPGNN_F_BF16), MPGNN_ENOTSUP, "hop_bwd: MPGNN_F_BF16 is not built; use MPGNN_F_TF32X3");
+  MPGNN_REQUIRE(!drop || (flags & MPGNN_F_RELU), MPGNN_ENOTSUP,
+                "hop_bwd: dropout without MPGNN_F_RELU is not built (the keep-mask is recovered from [y > 0])");
   const int64_t n = g->n;
   Workspace ws(ws_ptr, ws_bytes);
   (void)ws.take<float>(fwd_ws_floats(f_in, f_out));
@@ -113,7 +121,7 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   // g_z = g_y * [y > 0] * 1/(1-p).  With the activation bitmask and both tensor-core kernels available
   // the gating is fused into their operand loads (g_z is never materialised); otherwise one pass writes it.
   const bool tc_w = wgrad_tcgen05_supported(n, f_in, f_in, f_out, flags);
-  const bool tc_d = (flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16)) && proj_tcgen05_supported(n, f_out, 0, 2 * f_in, flags);
+  const bool tc_d = (flags & MPGNN_F_TF32X3) && proj_tcgen05_supported(n, f_out, 0, 2 * f_in, flags);
   const float scale = drop ? (float)(1.0 / (1.0 - p)) : 1.f;
   const float* gz_src = gy;
   const uint32_t* fused_mask = nullptr;

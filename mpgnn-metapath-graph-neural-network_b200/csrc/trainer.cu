@@ -112,6 +112,7 @@ struct Trainer {
   cudaGraphExec_t exec;
   cudaStream_t own_stream;   // capture is not allowed on the legacy default stream
   double cap_lr, cap_b1, cap_b2, cap_eps, cap_wd;
+  bool params_set;           // run()/evaluate() refuse to work on the recycled slab's stale bytes
 };
 
 static int64_t trainer_ws_bytes(const Trainer& t) {
@@ -249,6 +250,7 @@ int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int6
   MPGNN_REQUIRE(n_layers >= 1 && n_layers <= 8, MPGNN_ENOTSUP, "trainer: metapath length %lld outside [1,8]", (long long)n_layers);
   MPGNN_REQUIRE(f_in >= 1 && hidden >= 1 && classes >= 1 && classes <= 64 && n_train > 0 && n_val > 0, MPGNN_EINVAL, "trainer: bad sizes");
   MPGNN_REQUIRE(dropout_p >= 0.0 && dropout_p < 1.0, MPGNN_EINVAL, "trainer: dropout p=%g", dropout_p);
+  MPGNN_REQUIRE(!(flags & MPGNN_F_BF16), MPGNN_ENOTSUP, "trainer: MPGNN_F_BF16 is not built; use MPGNN_F_TF32X3");
   for (int64_t k = 0; k < n_layers; ++k)
     MPGNN_REQUIRE(h_rel[k] >= 0 && h_rel[k] < g->r, MPGNN_ERANGE, "trainer: relation %lld outside [0,%lld)", (long long)h_rel[k], (long long)g->r);
   Trainer* t = new Trainer();
@@ -285,6 +287,14 @@ int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int6
   }
   Carver carve{static_cast<char*>(t->slab)};
   trainer_layout(t, carve);
+  // a recycled slab holds another trainer's bytes: parameters, optimiser state and the epoch words start from zero
+  ce = cudaMemset(t->params, 0, (size_t)(reinterpret_cast<char*>(t->adam_v + t->n_params) - reinterpret_cast<char*>(t->params)));
+  if (ce == cudaSuccess) ce = cudaMemset(t->st, 0, sizeof(TrainerState));
+  if (ce != cudaSuccess) {
+    set_error("trainer: clearing the parameter block failed: %s", cudaGetErrorString(ce));
+    trainer_free(t);
+    return MPGNN_ECUDA;
+  }
   *out = t;
   return MPGNN_OK;
 }
@@ -295,7 +305,7 @@ static int trainer_forward(Trainer* t, bool train, cudaStream_t s) {
   const float* in = t->x;
   for (int k = 0; k < t->n_layers; ++k) {
     const int64_t fi = k == 0 ? t->f_in : H;
-    uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16));
+    uint32_t fl = MPGNN_F_RELU | (t->flags & MPGNN_F_TF32X3);
     if (train && t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
     MPGNN_PROPAGATE(hop_fwd(t->g, t->rel[k], in, fi, t->params + t->off_w[k], t->params + t->off_root[k],
                             t->params + t->off_bias[k], H, fl, t->dropout_p, t->seed, 0, nullptr, t->h[k], t->y[k],
@@ -368,7 +378,7 @@ static int trainer_backward(Trainer* t, cudaStream_t s) {
   for (int k = t->n_layers - 1; k >= 0; --k) {
     const int64_t fi = k == 0 ? t->f_in : H;
     const float* in = k == 0 ? t->x : t->y[k - 1];
-    uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_BF16));
+    uint32_t fl = MPGNN_F_RELU | (t->flags & MPGNN_F_TF32X3);
     if (t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
     if (k > 0) fl |= MPGNN_F_NEED_GX;
     MPGNN_PROPAGATE(hop_bwd(t->g, t->rel[k], in, t->h[k], t->y[k], reinterpret_cast<const uint32_t*>(t->am[k]), gy, fi, t->params + t->off_w[k],
@@ -401,6 +411,7 @@ static int trainer_epoch(Trainer* t, double lr, double b1, double b2, double eps
 int trainer_run(Trainer* t, int64_t epochs, double lr, double b1, double b2, double eps, double wd, int use_graph,
                 cudaStream_t s, double* h_trace, double* h_last_val_f1) {
   MPGNN_REQUIRE(t != nullptr && epochs >= 1, MPGNN_EINVAL, "trainer_run: bad arguments");
+  MPGNN_REQUIRE(t->params_set, MPGNN_EINVAL, "trainer_run: call mpgnn_trainer_set_params first");
   cudaStream_t caller = s;
   if (use_graph && (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread)) {
     // stream capture is not permitted on the default streams: run on a private stream, ordered after
@@ -453,6 +464,7 @@ int trainer_set_params(Trainer* t, const float* d_flat, cudaStream_t s) {
   MPGNN_CUDA_CHECK(cudaMemsetAsync(t->adam_m, 0, (size_t)t->n_params * 4, s));
   MPGNN_CUDA_CHECK(cudaMemsetAsync(t->adam_v, 0, (size_t)t->n_params * 4, s));
   MPGNN_CUDA_CHECK(cudaMemsetAsync(t->st, 0, sizeof(TrainerState), s));
+  t->params_set = true;
   return MPGNN_OK;
 }
 
@@ -471,6 +483,7 @@ int64_t trainer_num_params(const Trainer* t) { return t ? t->n_params : 0; }
 int trainer_evaluate(Trainer* t, const int64_t* d_idx, const int64_t* d_y, int64_t n_idx, cudaStream_t s, float* h_loss,
                      double* h_f1) {
   MPGNN_REQUIRE(t && d_idx && d_y && n_idx > 0, MPGNN_EINVAL, "trainer_evaluate: bad arguments");
+  MPGNN_REQUIRE(t->params_set, MPGNN_EINVAL, "trainer_evaluate: call mpgnn_trainer_set_params first");
   const int64_t *vi = t->val_idx, *vy = t->val_y, vn = t->n_val;
   t->val_idx = d_idx; t->val_y = d_y; t->n_val = n_idx;
   int rc = trainer_forward(t, false, s);

@@ -23,8 +23,10 @@ class RelationGraph:
             raise AssertionError("edge_type is required")  # reference: assert edge_type is not None (:195)
         if edge_type.numel() != edge_index.size(1):
             raise ValueError("edge_type must have one entry per edge")
-        if num_relations is None:
-            num_relations = int(edge_type.max().item()) + 1 if edge_type.numel() else 1
+        in_data = int(edge_type.max().item()) + 1 if edge_type.numel() else 1
+        # a relation id above every id in the data has no edges (reference: `edge_type == relation` is an empty mask,
+        # mp_rgcn_layer.py:231); ids the data does hold always get their bucket
+        num_relations = in_data if num_relations is None else max(int(num_relations), in_data)
         self.num_nodes, self.num_relations = int(num_nodes), int(num_relations)
         self.num_edges = int(edge_index.size(1))
         handle = ctypes.c_void_p()
@@ -95,7 +97,7 @@ _CACHE = {}
 _CACHE_MAX = 8
 
 
-def graph_for(edge_index, edge_type, num_nodes, device):
+def graph_for(edge_index, edge_type, num_nodes, device, num_relations=None):
     """Return the RelationGraph of (edge_index, edge_type), building it on first use.
 
     The reference treats edge_index/edge_type as immutable for a run (main.py:1245-1255), so
@@ -106,10 +108,12 @@ def graph_for(edge_index, edge_type, num_nodes, device):
     hit = _CACHE.get(key)
     if hit is not None:
         ei_ref, et_ref, g = hit
-        if ei_ref() is edge_index and et_ref() is edge_type:
+        if ei_ref() is edge_index and et_ref() is edge_type and (num_relations is None or
+                                                                  g.num_relations >= int(num_relations)):
             return g
-    # num_relations from the data (reference: relations are whatever ids edge_type holds)
-    g = RelationGraph(edge_index, edge_type, num_nodes, None, device)
+    # num_relations from the caller when it knows it (main() does: tot_rel), else from the data.  A relation id the
+    # edge list never uses simply has no edges (mp_rgcn_layer.py:231: an empty mask), see RelationGraph.covers().
+    g = RelationGraph(edge_index, edge_type, num_nodes, num_relations, device)
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (weakref.ref(edge_index), weakref.ref(edge_type), g)

@@ -29,26 +29,48 @@ class Data:
             setattr(self, k, v)
 
 
+_STAGED_ATTRS = ("x", "edge_index", "edge_type", "train_idx", "train_y", "val_idx", "val_y", "test_idx", "test_y")
+
+
 def _as_index(v, device):
     if isinstance(v, torch.Tensor):
         return v.to(device=device, dtype=torch.int64).contiguous()
     return torch.as_tensor(np.asarray(v, dtype=np.int64), device=device)
 
 
-def _staged(data, device):
-    """Device copies of the bag's tensors + the relation CSR, built once per (bag, device)."""
+def _staged(data, device, min_relations=None):
+    """Device copies of the bag's tensors + the relation CSR, built once per (bag, device).  `min_relations`: the
+    graph must have buckets for relation ids below it (ids the edge list never uses are empty relations)."""
     cache = getattr(data, "_b200_staged", None)
-    if cache is not None and cache["device"] == device and cache["x_src"] is data.x:
+    if (cache is not None and min_relations is not None and cache["graph"].num_relations < min_relations
+            and not isinstance(data.edge_index, RelationGraph)):
+        cache = None
+    # the bag's tensors are immutable for a run in the reference (main.py:1245-1255); should a caller swap one of them
+    # anyway, the identity of every staged attribute is part of the key, so stale device copies are never reused
+    srcs = tuple(getattr(data, k, None) for k in _STAGED_ATTRS)
+    if cache is not None and cache["device"] == device and len(cache["srcs"]) == len(srcs) and all(
+            a is b for a, b in zip(cache["srcs"], srcs)):
         return cache
     x = data.x.to(device=device, dtype=torch.float32).contiguous()
+    n = x.size(0)
     graph = data.edge_index if isinstance(data.edge_index, RelationGraph) else graph_for(
-        data.edge_index, data.edge_type, x.size(0), device)
-    cache = {"device": device, "x_src": data.x, "x": x, "graph": graph}
+        data.edge_index, data.edge_type, n, device, num_relations=min_relations)
+    cache = {"device": device, "srcs": srcs, "x": x, "graph": graph, "max_label": -1}
     for split in ("train", "val", "test"):
         idx = getattr(data, split + "_idx", None)
         if idx is not None:
-            cache[split + "_idx"] = _as_index(idx, device)
-            cache[split + "_y"] = _as_index(getattr(data, split + "_y"), device)
+            i, y = _as_index(idx, device), _as_index(getattr(data, split + "_y"), device)
+            if i.numel() != y.numel():
+                raise ValueError("%s_idx and %s_y differ in length (%d vs %d)" % (split, split, i.numel(), y.numel()))
+            if i.numel():
+                # validated once here: the device kernels index logp[idx * C + y] without a range check
+                lo, hi, ylo, yhi = (int(v) for v in torch.stack([i.min(), i.max(), y.min(), y.max()]).tolist())
+                if lo < 0 or hi >= n:
+                    raise ValueError("%s_idx holds node ids outside [0, %d)" % (split, n))
+                if ylo < 0:
+                    raise ValueError("%s_y holds negative labels" % split)
+                cache["max_label"] = max(cache["max_label"], yhi)
+            cache[split + "_idx"], cache[split + "_y"] = i, y
     data._b200_staged = cache
     return cache
 
@@ -119,9 +141,11 @@ class CandidateTrainer:
                  seed=None, precision="tf32x3", max_epochs=EPOCHS_PER_CANDIDATE):
         lib = _lib.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.st = _staged(data_mpgnn, self.device)
         self.metapath = [int(r) for r in metapath]
+        self.st = _staged(data_mpgnn, self.device, min_relations=max(self.metapath) + 1)
         self.dims = (int(input_dim), int(hidden_dim), int(ll_output_dim))
+        if self.st["max_label"] >= self.dims[2]:      # F.nll_loss raises here in the reference (main.py:1065)
+            raise ValueError("labels up to %d with ll_output_dim=%d" % (self.st["max_label"], self.dims[2]))
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         flags = _lib.F_TF32X3 if precision == "tf32x3" else 0
@@ -320,11 +344,14 @@ def main(args):
     else:
         raise NotImplementedError("dataset %r: only 'synthetic' and 'fb15k-237' are built" % args.dataset)
     results = []
+    final_dict = {}                                  # main.py:1208: ONE table for all one-vs-rest label sets
+    # the reference rebuilds these inside its loop (main.py:1231); they do not depend on the label set, and one pair of
+    # tensors means one CSR build for the whole run
+    edge_index, edge_type = D.get_edge_index_and_type_no_reverse(edges)
     for binary_lab in binary_labels:
         x = D.get_node_features(features)
         input_dim = x.size(1)
         ll_output_dim = 2 if args.dataset == "synthetic" else len(torch.unique(true_labels).tolist())
-        edge_index, edge_type = D.get_edge_index_and_type_no_reverse(edges)
         _, train_idx, train_y, test_idx, test_y, val_idx, val_y = D.splitting_node_and_labels(
             true_labels, features, sources, args.dataset)
         if args.dataset == "fb15k-237":
@@ -334,10 +361,18 @@ def main(args):
         data = Data(x=x, edge_index=edge_index, edge_type=edge_type, labels=binary_lab.unsqueeze(-1),
                     num_nodes=x.size(0), source_nodes_mask=list(sources))
         res = search.greedy_search(data, data_mpgnn, input_dim, args.hidden_dim, tot_rel, args.hidden_dim,
-                                   ll_output_dim, args.dataset, comm=comm, log=log)
+                                   ll_output_dim, args.dataset, comm=comm, log=log, final_dict=final_dict, select=False)
         results.append(res)
-        if comm.rank == 0:
-            print("final meta: ", res["final_meta"], "test acc: ", res["test_f1"])      # main.py:1476
+    # main.py:1463-1476: top 3 of the merged table and the greedy union, once, on the last label set's data_mpgnn
+    # (x, edges and split do not depend on the label set)
+    f_meta, test_f1 = [], 0.0
+    if results:
+        f_meta, test_f1 = search.final_selection(final_dict, search.make_union_fn(
+            data_mpgnn, input_dim, args.hidden_dim, tot_rel, args.hidden_dim, ll_output_dim))
+    for res in results:
+        res["final_meta"], res["test_f1"] = f_meta, test_f1
+    if comm.rank == 0:
+        print("final meta: ", f_meta, "test acc: ", test_f1)                             # main.py:1476
     return results
 
 

@@ -71,7 +71,7 @@ class MPNetm(torch.nn.Module):
     torch.manual_seed yields the same state_dict."""
 
     def __init__(self, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, n_metapaths, metapaths,
-                 device=None, precision="fp32"):
+                 device=None, precision="tf32x3"):
         super().__init__()
         self.n_metapaths = n_metapaths
         self.metapaths = metapaths
@@ -108,7 +108,8 @@ class MPNetm(torch.nn.Module):
         if isinstance(edge_index, RelationGraph):
             graph = edge_index
         else:
-            graph = graph_for(edge_index, edge_type, x.size(0), dev)
+            need = 1 + max((int(r) for mp in self.metapaths for r in mp), default=0)
+            graph = graph_for(edge_index, edge_type, x.size(0), dev, num_relations=need)
         x = x.to(device=dev, dtype=torch.float32).contiguous()
         embeddings = []
         for i, mp in enumerate(self.metapaths):

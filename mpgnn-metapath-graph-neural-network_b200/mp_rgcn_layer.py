@@ -113,8 +113,9 @@ class CustomRGCNConv(torch.nn.Module):
     """
 
     def __init__(self, in_channels, out_channels, num_relations, num_bases=None, num_blocks=None, aggr="mean",
-                 root_weight=True, bias=True, device=None, **kwargs):
+                 root_weight=True, bias=True, device=None, precision="tf32x3", **kwargs):
         super().__init__()
+        self.precision = precision
         kwargs.setdefault("aggr", aggr)
         if num_bases is not None and num_blocks is not None:
             raise ValueError("Can not apply both basis-decomposition and "
@@ -169,7 +170,11 @@ class CustomRGCNConv(torch.nn.Module):
 
     # -- internal: one hop with the epilogue MPNetm wants fused ---------------------------
     def hop(self, relation, x, graph, relu=False, dropout_p=0.0, dropout_mask=None, seed=None, offset=0,
-            precision="fp32"):
+            precision=None):
+        """`precision`: "tf32x3" (default, `self.precision`) = projection and weight gradient on tcgen05 with the
+        error-compensated 3xTF32 split (fp32-class, <= 2e-6 measured) wherever the shape is eligible, the exact-fp32
+        SIMT kernels otherwise; "fp32" = the SIMT kernels always."""
+        precision = self.precision if precision is None else precision
         if not self.weight.is_cuda:
             raise RuntimeError("CustomRGCNConv has no CPU path: move the module to a CUDA device")
         if self.root is None:
@@ -190,9 +195,12 @@ class CustomRGCNConv(torch.nn.Module):
         if precision == "tf32x3":
             flags |= _lib.F_TF32X3
         elif precision == "bf16":
-            flags |= _lib.F_BF16
+            raise NotImplementedError("precision='bf16' is not built (MPGNN_F_BF16 is rejected by the library)")
         elif precision != "fp32":
-            raise ValueError("precision must be 'fp32', 'tf32x3' or 'bf16'")
+            raise ValueError("precision must be 'fp32' or 'tf32x3'")
+        if (flags & (_lib.F_DROPOUT_MASK | _lib.F_DROPOUT_SEED)) and not relu:
+            raise NotImplementedError("dropout without relu is not built (MPNetm always applies relu first, "
+                                      "model.py:210-214)")
         return _HopFunction.apply(x, self.weight, self.root, self.bias, graph, int(relation), flags,
                                   float(dropout_p), seed or 0, offset, mask_bits)
 
@@ -206,7 +214,8 @@ class CustomRGCNConv(torch.nn.Module):
                 raise NotImplementedError("SparseTensor adjacency is not supported")
             assert edge_type is not None
             n = x.size(0)
-            graph = graph_for(edge_index, edge_type, n, self.weight.device)
+            # a relation id the edge list never uses is an empty neighbourhood, not an error (:231)
+            graph = graph_for(edge_index, edge_type, n, self.weight.device, num_relations=int(relation) + 1)
         return self.hop(relation, x, graph)
 
     def message(self, x_j):

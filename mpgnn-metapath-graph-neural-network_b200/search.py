@@ -542,14 +542,29 @@ def final_selection(final_dict, train_union_fn):
     return f_meta, old
 
 
+def make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim):
+    """The training `final_selection` runs per union of metapaths (main.py:1470): test macro-F1 under the candidate seed."""
+    from .main import mpgnn_parallel_multiple_x
+
+    def union_fn(metas):
+        torch.manual_seed(CANDIDATE_SEED)
+        return mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metas, True)
+    return union_fn
+
+
 def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, dataset, comm=None,
-                  score_fn=None, eval_fn=None, union_fn=None, bag_score_fn=None, log=None, max_depth=3):
-    """main.py:1289-1476.  `score_fn(data, rel)` -> (loss, edge_dict, dest_dict) or a bare loss,
+                  score_fn=None, eval_fn=None, union_fn=None, bag_score_fn=None, log=None, max_depth=3,
+                  final_dict=None, select=True):
+    """main.py:1289-1476.  `final_dict` (main.py:1208): the {str(metapath): validation F1} table; the reference creates
+    it ONCE before its loop over the one-vs-rest label sets and every label set's candidates are merged into it, so
+    the driver passes the same dict to every call with `select=False` and runs `final_selection` once after the
+    loop (main.py:1463-1476); with the defaults (one label set) the call does both.
+    `score_fn(data, rel)` -> (loss, edge_dict, dest_dict) or a bare loss,
     `bag_score_fn(bag_data, rel, metapath_len)` -> (rel, loss, model, predictions, skip),
     `eval_fn(meta)` -> validation macro-F1, `union_fn(metas)` -> test macro-F1 default to the device
     implementations; tests inject CPU stand-ins to exercise the fan-out and the rules.
     `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381)."""
-    from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_x, mpgnn_parallel_multiple_batch
+    from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_batch
     comm = comm or Comm()
     dict_fn = None
     if score_fn is None:
@@ -572,10 +587,7 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
             return mpgnn_parallel_multiple_batch(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
                                                  metas, seed=CANDIDATE_SEED)
     if union_fn is None:
-        def union_fn(metas):
-            torch.manual_seed(CANDIDATE_SEED)
-            return mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
-                                             metas, True)
+        union_fn = make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim)
     # ---- step 0: every rank scores its share of the relations (main.py:1319-1328) ----------
     actual_relations = node_types_and_connected_relations(data, BAGS=False, dataset=dataset)
     local = relation_split(actual_relations, comm.size, comm.rank)
@@ -645,7 +657,7 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
                     preds = {kk: list(vv) for kk, vv in res[3].items()}
                     preds = retrain_bags(data_copy, rel, preds, True, input_dim, dataset, metapath_len=len(meta))
                     src_mask, _ = relabel_nodes_inside_bags(preds, data_copy, res[2])
-                    e2, d2 = create_edge_dictionary(data_copy, rel, src_mask, BAGS=False, dataset="synthetic")
+                    e2, d2 = create_edge_dictionary(data_copy, rel, src_mask, BAGS=False, dataset=dataset)  # main.py:1433
                     e2, d2 = clean_dictionaries(data_copy, e2, d2, res[2])
                     state[str(tmp_meta)] = [e2, d2, data_copy]
             current_metapaths_list = [list(m) for m in intermediate]
@@ -666,13 +678,13 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
             done[key] = float(eval_fn(final_metapaths_list[i]))
         mine.append([float(i), done[key]])
     gathered = comm.allgather_records(mine, 2, max(1, len(final_metapaths_list)))
-    final_dict = {}
+    final_dict = {} if final_dict is None else final_dict
     for part in gathered:                                                    # rank order; later keys overwrite
         for i, f1 in part:
             final_dict[str(final_metapaths_list[int(i)])] = f1
     # ---- final selection (rank 0 in the reference; replicated here, it is deterministic) ----
-    f_meta, test_f1 = final_selection(final_dict, union_fn)
-    if log:
+    f_meta, test_f1 = final_selection(final_dict, union_fn) if select else (None, None)
+    if log and select:
         log("final meta: %s test acc: %s" % (f_meta, test_f1))
     return {"relations": step0["relations"], "losses": step0["losses"], "kept": best, "bag_steps": steps,
             "candidates": final_metapaths_list, "final_dict": final_dict, "final_meta": f_meta, "test_f1": test_f1}

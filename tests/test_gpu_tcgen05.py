@@ -288,3 +288,90 @@ torch.save(outs, sys.argv[1])
             assert (a != c).float().mean() < 1e-4          # the bitmask may differ where y is ~0 in one of the two
         else:
             assert rel_err(a, c) < TOL
+
+
+def _classes_of(fn):
+    """Kernel classes (ScopedTimer names) the library recorded while `fn` ran."""
+    lib = _lib.load()
+    lib.mpgnn_timing_reset()
+    lib.mpgnn_timing_enable(1)
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        lib.mpgnn_timing_enable(0)
+    return set(_lib.timing_collect())
+
+
+@pytest.mark.parametrize("n,f_in,f_out,eligible", [(40000, 128, 128, True), (5000, 64, 64, True), (3000, 32, 64, "proj"),
+                                                   (4000, 2, 64, False), (3000, 100, 64, False)])
+def test_default_path_runs_the_tcgen05_kernels(n, f_in, f_out, eligible):
+    """The reference-facing call conv(layer_num, relation, x, edge_index, edge_type) (mp_rgcn_layer.py:158-159) takes
+    the tensor-core kernels by default wherever the shape allows, and the SIMT kernels only as the odd-shape fallback;
+    which one ran is read from the library's own per-kernel-class timers, not inferred from the numbers."""
+    ei, et = _graph(n, 5 * n, 3, seed=7)
+    x = torch.randn(n, f_in, generator=torch.Generator().manual_seed(1))
+    torch.manual_seed(3)
+    conv = mpgnn_b200.CustomRGCNConv(f_in, f_out, 1, flow="target_to_source", device=DEV)
+    assert conv.precision == "tf32x3"
+    eid, etd = ei.to(DEV), et.to(DEV)
+    xi = x.to(DEV).requires_grad_(True)
+    out = {}
+
+    def run():
+        y = conv(0, 1, xi, eid, etd)
+        y.backward(torch.ones_like(y))
+        out["y"] = y
+
+    classes = _classes_of(run)
+    tc = {"proj_fwd_tcgen05", "wgrad_tn_tcgen05", "dgrad_nt_tcgen05"}
+    simt = {"proj_fwd_simt", "wgrad_tn_simt", "dgrad_nt_simt"}
+    if eligible is True:
+        assert tc <= classes and not (simt & classes), sorted(classes)
+    elif eligible == "proj":        # projection shapes eligible, weight-gradient shape (32-wide operand) not
+        assert {"proj_fwd_tcgen05", "dgrad_nt_tcgen05", "wgrad_tn_simt"} <= classes, sorted(classes)
+    else:
+        assert simt <= classes and not (tc & classes), sorted(classes)
+    # and the default path meets the fp32 bar against the oracle
+    w, root, b = conv.weight.detach().cpu(), conv.root.detach().cpu(), conv.bias.detach().cpu()
+    z, _, _ = orc.conv_forward(x, ei, et, 1, w, root, b)
+    assert rel_err(out["y"], z) <= TOL
+    # precision="fp32" keeps every kernel on the SIMT path
+    classes32 = _classes_of(lambda: conv.hop(1, xi.detach(), mpgnn_b200.graph_for(eid, etd, n, torch.device(DEV)),
+                                             precision="fp32"))
+    assert "proj_fwd_simt" in classes32 and not (tc & classes32), sorted(classes32)
+
+
+def test_model_default_path_runs_the_tcgen05_kernels(fx3):
+    """MPNetm at the reference's defaults (hidden 64): hidden layers and their gradients on tcgen05, the 2-wide input
+    layer on the thin SIMT kernels."""
+    torch.manual_seed(30)
+    model = mpgnn_b200.MPNetm(2, 64, fx3["num_relations"], 64, 2, 1, [[1, 0]], device=DEV)
+    assert model.precision == "tf32x3"
+    x, ei, et = fx3["x"].to(DEV), fx3["edge_index"].to(DEV), fx3["edge_type"].to(DEV)
+
+    def run():
+        model.train()
+        model(x, ei, et).sum().backward()
+
+    classes = _classes_of(run)
+    assert {"proj_fwd_tcgen05", "wgrad_tn_tcgen05", "dgrad_nt_tcgen05"} <= classes, sorted(classes)
+
+
+def test_bf16_flag_and_dropout_without_relu_are_rejected():
+    """MPGNN_F_BF16 is reserved (no kernel behind it) and dropout without relu cannot be differentiated from [y > 0]:
+    both are refused with MPGNN_ENOTSUP instead of silently running something else."""
+    n, f = 2048, 64
+    ei, et = _graph(n, 4 * n, 2, seed=1)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 2, device=DEV)
+    x = torch.randn(n, f, device=DEV)
+    w, root, b = torch.randn(f, f, device=DEV), torch.randn(f, f, device=DEV), torch.zeros(f, device=DEV)
+    with pytest.raises(NotImplementedError):
+        _fwd(graph, 0, x, w, root, b, _lib.F_RELU | _lib.F_BF16, None)
+    with pytest.raises(NotImplementedError):
+        _fwd(graph, 0, x, w, root, b, _lib.F_DROPOUT_SEED | _lib.F_TF32X3, None)
+    conv = mpgnn_b200.CustomRGCNConv(f, f, 1, flow="target_to_source", device=DEV)
+    with pytest.raises(NotImplementedError):
+        conv.hop(0, x, graph, relu=False, dropout_p=0.5)
+    with pytest.raises(NotImplementedError):
+        conv.hop(0, x, graph, relu=True, precision="bf16")
