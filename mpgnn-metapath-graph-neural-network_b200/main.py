@@ -327,10 +327,18 @@ def main(args):
     import os
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
+    n_dev = torch.cuda.device_count()
+    if n_dev < 1:
+        raise RuntimeError("mpgnn_b200.main needs a CUDA device (there is no CPU path)")
+    device = torch.device("cuda", local % n_dev)
+    torch.cuda.set_device(device)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=device)
+        # one process per GPU over NCCL; more processes than GPUs (the reference's `mpiexec -n P` on a small box) share
+        # the devices and exchange their few records over gloo -- NCCL refuses two ranks on one device
+        if int(os.environ.get("LOCAL_WORLD_SIZE", world)) <= n_dev:
+            dist.init_process_group("nccl", device_id=device)
+        else:
+            dist.init_process_group("gloo")
     comm = search.Comm(device)
     log = print if comm.rank == 0 else None
     # every rank reads the (small) files itself: nothing to broadcast (main.py:1211-1212, 1309)
@@ -361,14 +369,16 @@ def main(args):
         data = Data(x=x, edge_index=edge_index, edge_type=edge_type, labels=binary_lab.unsqueeze(-1),
                     num_nodes=x.size(0), source_nodes_mask=list(sources))
         res = search.greedy_search(data, data_mpgnn, input_dim, args.hidden_dim, tot_rel, args.hidden_dim,
-                                   ll_output_dim, args.dataset, comm=comm, log=log, final_dict=final_dict, select=False)
+                                   ll_output_dim, args.dataset, comm=comm, log=log, final_dict=final_dict, select=False,
+                                   max_depth=getattr(args, "max_depth", None) or 3, epochs=getattr(args, "epochs", None))
         results.append(res)
     # main.py:1463-1476: top 3 of the merged table and the greedy union, once, on the last label set's data_mpgnn
     # (x, edges and split do not depend on the label set)
     f_meta, test_f1 = [], 0.0
     if results:
         f_meta, test_f1 = search.final_selection(final_dict, search.make_union_fn(
-            data_mpgnn, input_dim, args.hidden_dim, tot_rel, args.hidden_dim, ll_output_dim))
+            data_mpgnn, input_dim, args.hidden_dim, tot_rel, args.hidden_dim, ll_output_dim,
+            epochs=getattr(args, "epochs", None)))
     for res in results:
         res["final_meta"], res["test_f1"] = f_meta, test_f1
     if comm.rank == 0:
@@ -387,6 +397,9 @@ def _parse_args(argv=None):
     parser.add_argument("--label_file", type=str, required=True, help="labels file")
     parser.add_argument("--relations_legend_file", type=str, required=False, help="relations legend file")
     parser.add_argument("--pickle_filename", type=str, required=False, help="pickle files")
+    # not in the reference (its values are hard-coded: 999 epochs main.py:1121, 3 bag iterations main.py:1381)
+    parser.add_argument("--epochs", type=int, required=False, help="epochs per candidate (reference: 999)")
+    parser.add_argument("--max_depth", type=int, required=False, help="bag iterations (reference: 3)")
     return parser.parse_args(argv)
 
 

@@ -386,6 +386,9 @@ def _bag_restart_loop(data, relation, features_dim, seed, max_restarts=None, dev
             rest += 1
         for node in frozen:
             grad_mask[node] = 0
+        if record is not None:
+            record.setdefault("frozen", []).append(list(frozen))
+            record.setdefault("w", []).append(trained_w.numpy().copy())
         weights = reinitialize_weights(data, destination_dictionary, trained_w, frozen)
     if record is not None:
         record.update(bags=bags, bag_labels=labels_list, dest_keys=list(destination_dictionary.keys()))
@@ -542,19 +545,20 @@ def final_selection(final_dict, train_union_fn):
     return f_meta, old
 
 
-def make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim):
+def make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, epochs=None):
     """The training `final_selection` runs per union of metapaths (main.py:1470): test macro-F1 under the candidate seed."""
-    from .main import mpgnn_parallel_multiple_x
+    from .main import mpgnn_parallel_multiple_x, EPOCHS_PER_CANDIDATE
 
     def union_fn(metas):
         torch.manual_seed(CANDIDATE_SEED)
-        return mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metas, True)
+        return mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metas, True,
+                                         epochs=epochs or EPOCHS_PER_CANDIDATE)
     return union_fn
 
 
 def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, dataset, comm=None,
                   score_fn=None, eval_fn=None, union_fn=None, bag_score_fn=None, log=None, max_depth=3,
-                  final_dict=None, select=True):
+                  final_dict=None, select=True, epochs=None):
     """main.py:1289-1476.  `final_dict` (main.py:1208): the {str(metapath): validation F1} table; the reference creates
     it ONCE before its loop over the one-vs-rest label sets and every label set's candidates are merged into it, so
     the driver passes the same dict to every call with `select=False` and runs `final_selection` once after the
@@ -564,7 +568,8 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     `eval_fn(meta)` -> validation macro-F1, `union_fn(metas)` -> test macro-F1 default to the device
     implementations; tests inject CPU stand-ins to exercise the fan-out and the rules.
     `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381)."""
-    from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_batch
+    from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_batch, EPOCHS_PER_CANDIDATE
+    epochs = epochs or EPOCHS_PER_CANDIDATE          # main.py:1121
     comm = comm or Comm()
     dict_fn = None
     if score_fn is None:
@@ -581,13 +586,14 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     if eval_fn is None:
         def eval_fn(meta):
             torch.manual_seed(CANDIDATE_SEED)
-            return mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, [meta])
+            return mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, [meta],
+                                           epochs=epochs)
 
         def batch_eval(metas):          # the rank's whole block at once: independent trainers run concurrently
             return mpgnn_parallel_multiple_batch(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
-                                                 metas, seed=CANDIDATE_SEED)
+                                                 metas, seed=CANDIDATE_SEED, epochs=epochs)
     if union_fn is None:
-        union_fn = make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim)
+        union_fn = make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, epochs=epochs)
     # ---- step 0: every rank scores its share of the relations (main.py:1319-1328) ----------
     actual_relations = node_types_and_connected_relations(data, BAGS=False, dataset=dataset)
     local = relation_split(actual_relations, comm.size, comm.rank)
@@ -682,6 +688,8 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     for part in gathered:                                                    # rank order; later keys overwrite
         for i, f1 in part:
             final_dict[str(final_metapaths_list[int(i)])] = f1
+    if log:
+        log("candidates: %s" % {k: round(v, 6) for k, v in final_dict.items()})
     # ---- final selection (rank 0 in the reference; replicated here, it is deterministic) ----
     f_meta, test_f1 = final_selection(final_dict, union_fn) if select else (None, None)
     if log and select:

@@ -159,8 +159,10 @@ class SyntheticGraph:
 
     @property
     def planted_relations(self):
-        """The ground-truth metapath as the search reports it (first hop first)."""
-        return [int(v) for v in self.meta_reversed[::-1]]
+        """The ground-truth metapath in the order the search reports it and MPNetm consumes it (main.py:1427 prepends,
+        layer k reads metapaths[i][k]): index 0 = the hop farthest from the labelled node, last = the relation leaving
+        it -- the order of metapath.dat's second line (the fixture's "1 0" is found as [1, 0])."""
+        return [int(v) for v in self.meta_reversed]
 
     def node_features(self):
         x = np.zeros((self.num_nodes, len(COLORS)), dtype=np.int64)

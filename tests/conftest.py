@@ -39,6 +39,22 @@ def fixture_as_torch(name="fixture_len3"):
         test_idx=g["test_idx"].astype(np.int64).tolist(), test_y=torch.from_numpy(g["test_y"].astype(np.int64)))
 
 
+def write_fixture_files(folder, name="fixture_len3"):
+    """node.dat / link.dat / label.dat in the reference's TSV formats (`id \\t f0 \\t f1`, `src \\t rel \\t dst`,
+    `id \\t label`), rewritten from a committed golden of the reference's own fixture folder (the folder itself does
+    not exist on the GPU box)."""
+    g = load_golden(name)
+    x, ei, et, lab = g["x"], g["edge_index"], g["edge_type"], g["labels"]
+    os.makedirs(folder, exist_ok=True)
+    with open(os.path.join(folder, "node.dat"), "w") as f:
+        f.write("".join("%d\t%s\n" % (i, "\t".join("%d" % v for v in row)) for i, row in enumerate(x)))
+    with open(os.path.join(folder, "link.dat"), "w") as f:
+        f.write("".join("%d\t%d\t%d\n" % (s, r, d) for s, r, d in zip(ei[0], et, ei[1])))
+    with open(os.path.join(folder, "label.dat"), "w") as f:
+        f.write("".join("%d\t%d\n" % (i, l) for i, l in enumerate(lab)))
+    return folder
+
+
 def rel_err(a, b):
     """Normalised max error: max|a-b| / max(|b|) -- the 'relative' of the 1e-5 fp32 bar."""
     a = torch.as_tensor(a, dtype=torch.float64).cpu()

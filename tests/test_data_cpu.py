@@ -50,3 +50,19 @@ def test_sn_zeroes_labelled_rows():
     x = torch.ones(6, 3)
     out = D.sn([0], [2], [5], x)
     assert out.sum(1).tolist() == [0, 3, 0, 3, 3, 0]
+
+
+def test_rewritten_fixture_files_round_trip_through_the_loaders(tmp_path):
+    """tests/test_gpu_cli.py feeds the CLI with TSV files rewritten from the committed golden (the reference's folder
+    does not travel to the GPU box): loading them must give back the golden's tensors exactly."""
+    from conftest import write_fixture_files, fixture_as_torch
+    from mpgnn_b200 import data as D
+    fx3 = fixture_as_torch("fixture_len3")
+    folder = write_fixture_files(str(tmp_path / "fx"))
+    labels, features, links, binary, tot = D.load_files(folder + "/node.dat", folder + "/link.dat", folder + "/label.dat")
+    assert torch.equal(D.get_node_features(features), fx3["x"])
+    ei, et = D.get_edge_index_and_type_no_reverse(links)
+    assert torch.equal(ei, fx3["edge_index"]) and torch.equal(et, fx3["edge_type"]) and tot == fx3["num_relations"]
+    assert torch.equal(labels, fx3["labels"])
+    _, train_idx, train_y, test_idx, test_y, val_idx, val_y = D.splitting_node_and_labels(labels, features, [], "synthetic")
+    assert list(train_idx) == fx3["train_idx"] and list(val_idx) == fx3["val_idx"] and list(test_idx) == fx3["test_idx"]

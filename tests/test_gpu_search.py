@@ -117,11 +117,18 @@ def test_k5_scorer_fb15k237_shape_with_source_mask_matches_oracle():
         opt = torch.optim.Adam([wt], lr=0.1)
         srcs = torch.unique(rows[mask[rows].bool()])
         ref = []
+        pos = torch.arange(rows.numel())
         for _ in range(25):
             opt.zero_grad()
+            # Score.forward (model.py:82-87): per source the FIRST maximum in edge order (python max/index), so the
+            # gradient goes to one destination even under ties (weights clamped to 0/1 tie often); torch's amax
+            # backward would split it
+            with torch.no_grad():
+                vmax = torch.full((n,), -1.0).scatter_reduce(0, rows, wt[cols], reduce="amax", include_self=True)
+                first = torch.full((n,), rows.numel(), dtype=torch.long).scatter_reduce(
+                    0, rows, torch.where(wt[cols] == vmax[rows], pos, rows.numel()), reduce="amin", include_self=True)
             pred = torch.zeros(n)
-            vals = torch.full((n,), -1.0).scatter_reduce(0, rows, wt[cols], reduce="amax", include_self=True)
-            pred[srcs] = vals[srcs]
+            pred[srcs] = wt[cols[first[srcs]]]
             sel = mask.bool()
             loss = ((pred[sel] - lab.float()[sel]) ** 2).mean()
             loss.backward()
@@ -129,4 +136,5 @@ def test_k5_scorer_fb15k237_shape_with_source_mask_matches_oracle():
             with torch.no_grad():
                 wt.clamp_(0.0, 1.0)
             ref.append(float(loss))
-        assert np.allclose(traj.numpy()[:1], ref[:1], rtol=1e-5, atol=1e-8), (rel, traj[:3], ref[:3])
+        assert np.allclose(traj.numpy(), ref, rtol=1e-4, atol=1e-8), (rel, traj[-3:], ref[-3:])   # the whole trajectory
+        assert arg.cpu()[srcs].tolist() == cols[first[srcs]].tolist()                            # last forward's argmax

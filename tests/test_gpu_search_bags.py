@@ -45,10 +45,23 @@ def test_bag_scorer_matches_reference_golden(fx3, rel0):
         assert bool(skip) == bool(g[tag + "skip"])
         ref = g[tag + "loss_traj"]
         got = np.array(rec["traj"])
-        # first restart: same initial weights (same RNG seam), so the trajectory must agree closely
-        assert np.allclose(got[:50], ref[:50], rtol=2e-3, atol=1e-6), (got[:5], ref[:5])
-        assert abs(loss - float(g[tag + "loss"])) <= max(2e-4, 0.05 * float(g[tag + "loss"]))
+        # EVERY restart, not only the first: same number of restarts, the whole loss trajectory at the 1e-4 bar (the
+        # absolute floor covers losses that train to ~1e-9, where a relative error says nothing), the trained weights
+        # after each restart, the Linear weight, and the freeze sets -- exactly, they steer the next restart's draws
+        n_restarts = int(g[tag + "n_restarts"])
+        assert len(got) == len(ref) == 50 * n_restarts
+        assert np.allclose(got, ref, rtol=1e-4, atol=1e-7), float(np.abs(got - ref).max())
+        fz_ptr, fz_flat = g[tag + "frozen_ptr"], g[tag + "frozen_flat"]
+        keys = g[tag + "dest_keys"]
+        for k in range(n_restarts):
+            assert rec["frozen"][k] == fz_flat[fz_ptr[k]:fz_ptr[k + 1]].tolist(), (tag, k)
+            assert np.allclose(rec["w"][k][keys], g[tag + "w_hist"][k], atol=2e-6), (tag, k)
+            assert np.allclose(rec["lin"][k], g[tag + "lin_hist"][2 * k + 1], atol=2e-6), (tag, k)
+        assert abs(loss - float(g[tag + "loss"])) <= 1e-4 * float(g[tag + "loss"]) + 1e-8
         assert list(preds.keys()) == g[tag + "pred_keys"].tolist()
+        pp, pv = g[tag + "pred_ptr"], g[tag + "pred_vals"]
+        for i, key in enumerate(preds):                                  # per-source predictions of every restart
+            assert np.allclose(preds[key], pv[pp[i]:pp[i + 1]], atol=1e-5), (tag, key)
 
 
 def test_greedy_search_recovers_ground_truth_metapath(fx3):

@@ -137,3 +137,65 @@ def test_planted_metapath_of_a_generated_graph_scores_highest():
     assert f1[0] > 0.95, f1
     assert f1[1] < f1[0] - 0.03, f1
     assert f1[2] < 0.6, f1
+
+
+@pytest.mark.parametrize("name,meta", [("m10", [1, 0]), ("m0", [0]), ("m23", [2, 3])])
+def test_trainer_999_epoch_score_matches_reference_golden(fx3, name, meta):
+    """What the selection consumes (main.py:1134: the LAST epoch's validation macro-F1 after 999 epochs, and the test
+    macro-F1 of main.py:1112) against the unmodified reference's 999-epoch dropout-free runs for the ground-truth
+    metapath, a one-hop candidate and an unrelated one (tests/golden/make_golden.py: torch.manual_seed(30), p = 0)."""
+    g = load_golden("model_len3")
+    data = _bag(fx3)
+    ref, ref_test = g["trace999_" + name], g["trace999_%s_test" % name]
+    torch.manual_seed(30)
+    model = mpgnn_b200.MPNetm(2, 64, fx3["num_relations"], 64, 2, 1, [meta], device="cpu")
+    if name == "m10":
+        for k, v in _sd(g, "sd0.").items():
+            assert torch.equal(model.state_dict()[k], v), k       # same seed, same draw order as the reference
+    tr = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, meta, dropout_p=0.0, max_epochs=999)
+    tr.load_state_dict(model.state_dict())
+    trace = tr.run(999)
+    dev_loss = np.abs(trace[:, 0] - ref[:, 0]) / np.abs(ref[:, 0])
+    print("%s: train-loss rel dev max over epochs 1-100 %.2e, 1-999 %.2e; last val F1 ours %.6f ref %.6f"
+          % (name, dev_loss[:100].max(), dev_loss.max(), trace[-1, 3], ref[-1, 3]))
+    assert np.allclose(trace[:100, 0], ref[:100, 0], rtol=1e-3)              # early trajectory: fp32-class agreement
+    assert np.allclose(trace[:100, 1], ref[:100, 1], rtol=1e-3)
+    assert np.allclose(trace[:, 0], ref[:, 0], rtol=5e-2, atol=1e-4)         # whole run: same optimisation path
+    one_node = 1.5 / min(len(fx3["val_idx"]), len(fx3["test_idx"]))           # macro-F1 moves ~1/n per flipped node
+    assert abs(tr.last_val_f1 - ref[-1, 3]) <= 2 * one_node, (tr.last_val_f1, ref[-1, 3])
+    assert abs(trace[-1, 2] - ref[-1, 2]) <= 2 * one_node                    # train macro-F1, last epoch
+    loss_t, f1_t = tr.evaluate("test")
+    assert abs(f1_t - ref_test[1]) <= 2 * one_node, (f1_t, ref_test[1])
+    assert abs(loss_t - ref_test[0]) <= 5e-2 * abs(ref_test[0]) + 1e-4
+
+
+def test_trainer_c2_shape_trace_matches_oracle():
+    """BASELINE configs[1] shape (generated graph, 100k nodes, 10 relations, planted length-3 metapath, hidden 64):
+    30 dropout-free epochs of the native trainer against the CPU oracle's restatement of mpgnn_train /
+    mpgnn_validation (oracle/mpgnn_oracle.py: score_candidate) from the same initial state_dict."""
+    from oracle import mpgnn_oracle as orc
+    from mpgnn_b200 import synthetic
+    sg = synthetic.generate(100_000, 10, "red-blue-red-blue", 0, 2, seed=1)
+    x, ei, et, y = sg.tensors()
+    n = sg.num_nodes
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1))
+    n_te, n_va = n // 10, (n - n // 10) // 5
+    idx = {"test": perm[:n_te], "val": perm[n_te:n_te + n_va], "train": perm[n_te + n_va:]}
+    data = mpgnn_b200.Data(x=x, edge_index=ei, edge_type=et, num_nodes=n,
+                           **{k + "_idx": v for k, v in idx.items()}, **{k + "_y": y[v] for k, v in idx.items()})
+    meta = sg.planted_relations
+    torch.manual_seed(30)
+    sd = orc.mpnetm_init(2, 64, 2, [meta])
+    epochs = 30
+    bag = {"x": x, "edge_index": ei, "edge_type": et, "train_idx": idx["train"].tolist(), "train_y": y[idx["train"]],
+           "val_idx": idx["val"].tolist(), "val_y": y[idx["val"]]}
+    ref = np.array(orc.score_candidate(sd, bag, [meta], epochs=epochs, return_trace=True)[2])
+    tr = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, meta, dropout_p=0.0, max_epochs=epochs)
+    tr.load_state_dict(sd)
+    trace = tr.run(epochs)[:epochs]
+    print("C2 trace: train-loss rel dev max %.2e, val-loss %.2e, val-F1 abs dev max %.2e"
+          % ((np.abs(trace[:, 0] - ref[:, 0]) / np.abs(ref[:, 0])).max(),
+             (np.abs(trace[:, 1] - ref[:, 1]) / np.abs(ref[:, 1])).max(), np.abs(trace[:, 3] - ref[:, 3]).max()))
+    assert np.allclose(trace[:, 0], ref[:, 0], rtol=1e-4)
+    assert np.allclose(trace[:, 1], ref[:, 1], rtol=1e-4)
+    assert np.allclose(trace[:, 2:], ref[:, 2:], atol=5e-4)
