@@ -184,28 +184,44 @@ int mpgnn_score_bags(const mpgnn_graph* g, int64_t relation, const int32_t* d_ba
                      void* d_workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- device-resident candidate trainer -------------------------------------------------
- * mpgnn_parallel_multiple (main.py:1117-1134) for ONE metapath: builds the MPNetm stack
- * (model.py:179-228: one conv per hop, relu + dropout, fc1, relu, fc2, log_softmax), then
- * run() performs `epochs` x (mpgnn_train, mpgnn_validation) -- forward, nll on the train index,
- * backward, Adam, eval forward, validation nll, macro-F1 on train and validation -- on the device,
- * the whole epoch captured once in a CUDA graph (use_graph != 0).  Parameters are exchanged as one
- * flat fp32 array in state_dict order with torch layouts: per hop weight[f_in,H], root[f_in,H],
- * bias[H]; fc1.weight[H,H], fc1.bias[H], fc2.weight[C,H], fc2.bias[C].  set_params also resets the
- * optimiser state and the epoch counter.  h_trace (may be NULL) receives [epochs_done][4] doubles:
- * train loss, validation loss, train macro-F1, validation macro-F1 per epoch; *h_last_val_f1 is
- * what the reference returns.  d_x and the index arrays must stay alive while the trainer is used. */
+ * mpgnn_parallel_multiple / mpgnn_parallel_multiple_x (main.py:1117-1160): builds the MPNetm stack
+ * (model.py:179-228: per metapath one conv per hop with relu + dropout; the metapaths' embeddings
+ * concatenated; fc1, relu, fc2, log_softmax), then run() performs `epochs` x (mpgnn_train,
+ * mpgnn_validation) -- forward, nll on the train index, backward, Adam, eval forward, validation
+ * nll, macro-F1 on train and validation -- on the device, the whole epoch captured once in a CUDA
+ * graph.  mpgnn_trainer_create takes ONE metapath (h_relations[n_layers], layer k consumes
+ * h_relations[k]); mpgnn_trainer_create_multi takes n_paths of them, flattened, metapath i =
+ * h_relations[h_path_ptr[i] .. h_path_ptr[i+1]).  Parameters are exchanged as one flat fp32 array in
+ * state_dict order with torch layouts: per metapath, per hop weight[f_in,H], root[f_in,H], bias[H];
+ * then fc1.weight[H, H*n_paths], fc1.bias[H], fc2.weight[C,H], fc2.bias[C].  set_params also resets
+ * the optimiser state and the epoch counter and must precede run().  The first layer's aggregation
+ * mean_r(x) does not depend on the parameters and is computed once per trainer, not per epoch.
+ * run(): `mode` bit 0 = replay the epoch as a CUDA graph; bit 1 (MPGNN_TRAINER_VALIDATE_LAST) = run
+ * the validation pass only in the last epoch of the call (the reference validates every epoch and
+ * returns the last result; the pass has no side effects, so the returned number is the same).
+ * h_trace (may be NULL) receives [epochs_done][4] doubles: train loss, validation loss, train
+ * macro-F1, validation macro-F1 per epoch (NaN in the last three for epochs that skipped the
+ * validation); *h_last_val_f1 is what the reference returns.  d_x and the index arrays must stay
+ * alive while the trainer is used. */
+#define MPGNN_TRAINER_GRAPH 1
+#define MPGNN_TRAINER_VALIDATE_LAST 2
 typedef struct mpgnn_trainer mpgnn_trainer;
 int mpgnn_trainer_create(const mpgnn_graph* g, const float* d_x, int64_t f_in, int64_t hidden, int64_t num_classes,
                          const int64_t* h_relations, int64_t n_layers, const int64_t* d_train_idx,
                          const int64_t* d_train_y, int64_t n_train, const int64_t* d_val_idx, const int64_t* d_val_y,
                          int64_t n_val, double dropout_p, uint64_t seed, uint32_t flags, int64_t max_epochs,
                          mpgnn_trainer** out);
+int mpgnn_trainer_create_multi(const mpgnn_graph* g, const float* d_x, int64_t f_in, int64_t hidden, int64_t num_classes,
+                               const int64_t* h_relations, const int64_t* h_path_ptr, int64_t n_paths,
+                               const int64_t* d_train_idx, const int64_t* d_train_y, int64_t n_train,
+                               const int64_t* d_val_idx, const int64_t* d_val_y, int64_t n_val, double dropout_p,
+                               uint64_t seed, uint32_t flags, int64_t max_epochs, mpgnn_trainer** out);
 void mpgnn_trainer_free(mpgnn_trainer* t);
 int64_t mpgnn_trainer_num_params(const mpgnn_trainer* t);
 int mpgnn_trainer_set_params(mpgnn_trainer* t, const float* d_flat, void* stream);
 int mpgnn_trainer_get_params(const mpgnn_trainer* t, float* d_flat, void* stream);
 int mpgnn_trainer_run(mpgnn_trainer* t, int64_t epochs, double lr, double beta1, double beta2, double eps,
-                      double weight_decay, int use_graph, void* stream, double* h_trace, double* h_last_val_f1);
+                      double weight_decay, int mode, void* stream, double* h_trace, double* h_last_val_f1);
 /* nll + macro-F1 of the current parameters on another index set (mpgnn_test, main.py:1102-1115) */
 int mpgnn_trainer_evaluate(mpgnn_trainer* t, const int64_t* d_idx, const int64_t* d_y, int64_t n_idx, void* stream,
                            float* h_loss, double* h_f1);

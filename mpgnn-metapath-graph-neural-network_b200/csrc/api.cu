@@ -87,7 +87,7 @@ int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out);
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
             const uint8_t* mask_bits, float* h, float* y, uint32_t* actmask, void* ws_ptr, int64_t ws_bytes,
-            cudaStream_t s, const uint64_t* offset_ptr);
+            cudaStream_t s, const uint64_t* offset_ptr, bool h_precomputed);
 int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float* h, const float* y,
             const uint32_t* actmask, const float* gy, int64_t f_in, const float* w, const float* root, int64_t f_out,
             uint32_t flags, double p, float* gx, float* gw, float* groot, float* gbias, void* ws_ptr, int64_t ws_bytes,
@@ -113,9 +113,9 @@ int score_bags(const mpgnn_graph_impl* g, int64_t rel, const int32_t* bag_ptr, c
                float* diff, float* src_val, void* ws_ptr, int64_t ws_bytes, cudaStream_t s);
 struct Trainer;
 int trainer_create(const mpgnn_graph_impl* g, const float* x, int64_t f_in, int64_t hidden, int64_t classes,
-                   const int64_t* h_rel, int64_t n_layers, const int64_t* train_idx, const int64_t* train_y,
-                   int64_t n_train, const int64_t* val_idx, const int64_t* val_y, int64_t n_val, double dropout_p,
-                   uint64_t seed, uint32_t flags, int64_t max_epochs, Trainer** out);
+                   const int64_t* h_rel, const int64_t* h_path_ptr, int64_t n_paths, const int64_t* train_idx,
+                   const int64_t* train_y, int64_t n_train, const int64_t* val_idx, const int64_t* val_y, int64_t n_val,
+                   double dropout_p, uint64_t seed, uint32_t flags, int64_t max_epochs, Trainer** out);
 void trainer_free(Trainer* t);
 int64_t trainer_num_params(const Trainer* t);
 int trainer_set_params(Trainer* t, const float* d_flat, cudaStream_t s);
@@ -254,7 +254,7 @@ int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int6
                   uint64_t seed, uint64_t offset, const uint8_t* d_mask_bits, float* d_h, float* d_y,
                   uint32_t* d_actmask, void* d_workspace, int64_t workspace_bytes, void* stream) {
   return hop_fwd(impl(g), relation, d_x, f_in, d_w, d_root, d_bias, f_out, flags, dropout_p, seed, offset,
-                 d_mask_bits, d_h, d_y, d_actmask, d_workspace, workspace_bytes, stream_of(stream), nullptr);
+                 d_mask_bits, d_h, d_y, d_actmask, d_workspace, workspace_bytes, stream_of(stream), nullptr, false);
 }
 
 int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, const float* d_h, const float* d_y,
@@ -361,9 +361,18 @@ int mpgnn_trainer_create(const mpgnn_graph* g, const float* d_x, int64_t f_in, i
                          const int64_t* d_train_y, int64_t n_train, const int64_t* d_val_idx, const int64_t* d_val_y,
                          int64_t n_val, double dropout_p, uint64_t seed, uint32_t flags, int64_t max_epochs,
                          mpgnn_trainer** out) {
+  const int64_t path_ptr[2] = {0, n_layers};
+  return mpgnn_trainer_create_multi(g, d_x, f_in, hidden, num_classes, h_relations, path_ptr, 1, d_train_idx, d_train_y,
+                                    n_train, d_val_idx, d_val_y, n_val, dropout_p, seed, flags, max_epochs, out);
+}
+int mpgnn_trainer_create_multi(const mpgnn_graph* g, const float* d_x, int64_t f_in, int64_t hidden, int64_t num_classes,
+                               const int64_t* h_relations, const int64_t* h_path_ptr, int64_t n_paths,
+                               const int64_t* d_train_idx, const int64_t* d_train_y, int64_t n_train,
+                               const int64_t* d_val_idx, const int64_t* d_val_y, int64_t n_val, double dropout_p,
+                               uint64_t seed, uint32_t flags, int64_t max_epochs, mpgnn_trainer** out) {
   Trainer* t = nullptr;
-  int rc = trainer_create(impl(g), d_x, f_in, hidden, num_classes, h_relations, n_layers, d_train_idx, d_train_y,
-                          n_train, d_val_idx, d_val_y, n_val, dropout_p, seed, flags, max_epochs, &t);
+  int rc = trainer_create(impl(g), d_x, f_in, hidden, num_classes, h_relations, h_path_ptr, n_paths, d_train_idx,
+                          d_train_y, n_train, d_val_idx, d_val_y, n_val, dropout_p, seed, flags, max_epochs, &t);
   if (rc == MPGNN_OK) *out = reinterpret_cast<mpgnn_trainer*>(t);
   return rc;
 }
@@ -376,8 +385,8 @@ int mpgnn_trainer_get_params(const mpgnn_trainer* t, float* d_flat, void* stream
   return trainer_get_params(reinterpret_cast<const Trainer*>(t), d_flat, stream_of(stream));
 }
 int mpgnn_trainer_run(mpgnn_trainer* t, int64_t epochs, double lr, double beta1, double beta2, double eps,
-                      double weight_decay, int use_graph, void* stream, double* h_trace, double* h_last_val_f1) {
-  return trainer_run(reinterpret_cast<Trainer*>(t), epochs, lr, beta1, beta2, eps, weight_decay, use_graph,
+                      double weight_decay, int mode, void* stream, double* h_trace, double* h_last_val_f1) {
+  return trainer_run(reinterpret_cast<Trainer*>(t), epochs, lr, beta1, beta2, eps, weight_decay, mode,
                      stream_of(stream), h_trace, h_last_val_f1);
 }
 int mpgnn_trainer_evaluate(mpgnn_trainer* t, const int64_t* d_idx, const int64_t* d_y, int64_t n_idx, void* stream,

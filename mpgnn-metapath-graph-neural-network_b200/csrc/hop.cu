@@ -37,7 +37,7 @@ int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
             const uint8_t* mask_bits, float* h, float* y, uint32_t* actmask, void* ws_ptr, int64_t ws_bytes,
-            cudaStream_t s, const uint64_t* offset_ptr) {
+            cudaStream_t s, const uint64_t* offset_ptr, bool h_precomputed) {
   MPGNN_REQUIRE(g && x && w && root && h && y, MPGNN_EINVAL, "hop_fwd: NULL argument");
   MPGNN_REQUIRE(rel >= 0 && rel < g->r, MPGNN_ERANGE, "hop_fwd: relation %lld outside [0,%lld)", (long long)rel,
                 (long long)g->r);
@@ -57,7 +57,7 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   float* bp = ws.take<float>(fwd_ws_floats(f_in, f_out));
   MPGNN_REQUIRE(bp != nullptr, MPGNN_EINVAL, "hop_fwd: workspace too small");
 
-  {
+  if (!h_precomputed) {      // the caller may hold mean_r(x) already (first layer of a model: x is a constant)
     ScopedTimer tm("spmm_mean_fwd", s);
     MPGNN_PROPAGATE(launch_spmm_graph(g, rel, /*transpose=*/0, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));
   }

@@ -134,40 +134,60 @@ def mpgnn_test(model, data, class_weight):
 
 
 class CandidateTrainer:
-    """Device-resident training of ONE candidate metapath (the native `mpgnn_trainer_*` entry points):
-    the 999 x (mpgnn_train, mpgnn_validation) loop of main.py:1117-1134 as CUDA-graph replays."""
+    """Device-resident training of ONE candidate model (the native `mpgnn_trainer_*` entry points): the
+    999 x (mpgnn_train, mpgnn_validation) loop of main.py:1117-1160 as CUDA-graph replays.  `metapath` is one metapath
+    (list of relation ids, what mpgnn_parallel_multiple trains) or a list of metapaths (the unions
+    mpgnn_parallel_multiple_x trains for the final selection, model.py:203-220)."""
 
     def __init__(self, data_mpgnn, input_dim, hidden_dim, ll_output_dim, metapath, device=None, dropout_p=0.6,
                  seed=None, precision="tf32x3", max_epochs=EPOCHS_PER_CANDIDATE):
         lib = _lib.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.metapath = [int(r) for r in metapath]
-        self.st = _staged(data_mpgnn, self.device, min_relations=max(self.metapath) + 1)
+        if len(metapath) and isinstance(metapath[0], (int, np.integer)):
+            metapath = [metapath]
+        self.metapaths = [[int(r) for r in mp] for mp in metapath]
+        self.metapath = self.metapaths[0]
+        self.st = _staged(data_mpgnn, self.device, min_relations=max(r for mp in self.metapaths for r in mp) + 1)
         self.dims = (int(input_dim), int(hidden_dim), int(ll_output_dim))
         if self.st["max_label"] >= self.dims[2]:      # F.nll_loss raises here in the reference (main.py:1065)
             raise ValueError("labels up to %d with ll_output_dim=%d" % (self.st["max_label"], self.dims[2]))
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if precision not in ("tf32x3", "fp32"):
+            raise ValueError("precision must be 'fp32' or 'tf32x3'")
         flags = _lib.F_TF32X3 if precision == "tf32x3" else 0
-        rel = np.asarray(self.metapath, dtype=np.int64)
+        rel = np.asarray([r for mp in self.metapaths for r in mp], dtype=np.int64)
+        path_ptr = np.cumsum([0] + [len(mp) for mp in self.metapaths]).astype(np.int64)
         handle = ctypes.c_void_p()
         st = self.st
         with torch.cuda.device(self.device):
-            _lib.check(lib.mpgnn_trainer_create(
+            _lib.check(lib.mpgnn_trainer_create_multi(
                 st["graph"].handle, _lib.ptr(st["x"]), self.dims[0], self.dims[1], self.dims[2],
-                rel.ctypes.data_as(ctypes.c_void_p), len(rel), _lib.ptr(st["train_idx"]), _lib.ptr(st["train_y"]),
-                st["train_idx"].numel(), _lib.ptr(st["val_idx"]), _lib.ptr(st["val_y"]), st["val_idx"].numel(),
-                float(dropout_p), int(seed), flags, int(max_epochs), ctypes.byref(handle)))
+                rel.ctypes.data_as(ctypes.c_void_p), path_ptr.ctypes.data_as(ctypes.c_void_p), len(self.metapaths),
+                _lib.ptr(st["train_idx"]), _lib.ptr(st["train_y"]), st["train_idx"].numel(), _lib.ptr(st["val_idx"]),
+                _lib.ptr(st["val_y"]), st["val_idx"].numel(), float(dropout_p), int(seed), flags, int(max_epochs),
+                ctypes.byref(handle)))
         self._handle = handle
         self.max_epochs = int(max_epochs)
         self.num_params = int(lib.mpgnn_trainer_num_params(handle))
         self._finalizer = weakref.finalize(self, lib.mpgnn_trainer_free, handle)
 
+    def _layout(self):
+        """state_dict keys and shapes in MPNetm's order (model.py:180-201)."""
+        f_in, h, c = self.dims
+        keys, shapes = [], []
+        for i, mp in enumerate(self.metapaths):
+            for k in range(len(mp)):
+                fi = f_in if k == 0 else h
+                keys += ["layers_list.%d.%d.weight" % (i, k), "layers_list.%d.%d.root" % (i, k),
+                         "layers_list.%d.%d.bias" % (i, k)]
+                shapes += [(fi, h), (fi, h), (h,)]
+        keys += ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+        shapes += [(h, h * len(self.metapaths)), (h,), (c, h), (c,)]
+        return keys, shapes
+
     def _keys(self):
-        keys = []
-        for k in range(len(self.metapath)):
-            keys += ["layers_list.0.%d.weight" % k, "layers_list.0.%d.root" % k, "layers_list.0.%d.bias" % k]
-        return keys + ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+        return self._layout()[0]
 
     def load_state_dict(self, sd):
         """Parameters in MPNetm's state_dict layout; also resets Adam and the epoch counter."""
@@ -178,30 +198,28 @@ class CandidateTrainer:
             torch.cuda.current_stream().synchronize()
 
     def state_dict(self):
-        f_in, h, c = self.dims
         flat = torch.empty(self.num_params, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().mpgnn_trainer_get_params(self._handle, _lib.ptr(flat), _lib.current_stream()))
         flat = flat.cpu()
         out, off = {}, 0
-        shapes = []
-        for k in range(len(self.metapath)):
-            fi = f_in if k == 0 else h
-            shapes += [(fi, h), (fi, h), (h,)]
-        shapes += [(h, h), (h,), (c, h), (c,)]
-        for key, shp in zip(self._keys(), shapes):
+        for key, shp in zip(*self._layout()):
             cnt = int(np.prod(shp))
             out[key] = flat[off:off + cnt].view(*shp).clone()
             off += cnt
         return out
 
-    def run(self, epochs, lr=ADAM_LR, weight_decay=ADAM_WEIGHT_DECAY, use_graph=True):
-        """-> float64 array [epochs done so far, 4]: train loss, val loss, train macro-F1, val macro-F1."""
+    def run(self, epochs, lr=ADAM_LR, weight_decay=ADAM_WEIGHT_DECAY, use_graph=True, validate_every_epoch=True):
+        """-> float64 array [epochs done so far, 4]: train loss, val loss, train macro-F1, val macro-F1.
+        `validate_every_epoch=False`: the validation pass (no side effects: eval mode, no_grad, no random numbers) runs
+        only in the last epoch of this call -- the one whose result mpgnn_parallel_multiple returns (main.py:1134);
+        the skipped epochs hold NaN in the last three columns."""
         trace = np.zeros((self.max_epochs, 4), dtype=np.float64)
         last = ctypes.c_double()
+        mode = (1 if use_graph else 0) | (0 if validate_every_epoch else 2)
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().mpgnn_trainer_run(self._handle, int(epochs), float(lr), 0.9, 0.999, 1e-8,
-                                                     float(weight_decay), int(bool(use_graph)), _lib.current_stream(),
+                                                     float(weight_decay), mode, _lib.current_stream(),
                                                      trace.ctypes.data_as(ctypes.c_void_p), ctypes.byref(last)))
         self.last_val_f1 = float(last.value)
         return trace
@@ -215,15 +233,20 @@ class CandidateTrainer:
         return float(loss.value), float(f1.value)
 
 
-def _train_candidate_native(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths, epochs):
-    """Single-metapath candidate on the native trainer.  The model is constructed on the CPU first so
-    that the parameter draw follows the reference's RNG order (model.py:180-201)."""
-    model = MPNetm(input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, 1, metapaths, device="cpu")
+def _native_ok(metapaths):
+    return 1 <= len(metapaths) <= 8 and all(1 <= len(mp) <= 8 for mp in metapaths) and sum(len(mp) for mp in metapaths) <= 32
+
+
+def _train_candidate_native(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths, epochs,
+                            validate_every_epoch=False):
+    """One candidate model on the native trainer.  The model is constructed on the CPU first so that the parameter
+    draw follows the reference's RNG order (model.py:180-201).  Only the last epoch's validation result leaves the
+    call (main.py:1134), so the intermediate validation passes are skipped unless asked for."""
+    model = MPNetm(input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, len(metapaths), metapaths, device="cpu")
     p = model.dropout.p
-    tr = CandidateTrainer(data_mpgnn, input_dim, hidden_dim, ll_output_dim, metapaths[0], dropout_p=p,
-                          max_epochs=epochs)
+    tr = CandidateTrainer(data_mpgnn, input_dim, hidden_dim, ll_output_dim, metapaths, dropout_p=p, max_epochs=epochs)
     tr.load_state_dict(model.state_dict())
-    tr.run(epochs)
+    tr.run(epochs, validate_every_epoch=validate_every_epoch)
     return tr
 
 
@@ -241,8 +264,9 @@ def _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_
 def mpgnn_parallel_multiple(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,
                             epochs=EPOCHS_PER_CANDIDATE, native=True):
     """main.py:1117-1134 -- one candidate scored: 999 x (train, validation); returns the LAST
-    epoch's validation macro-F1."""
-    if native and len(metapaths) == 1 and 1 <= len(metapaths[0]) <= 8:
+    epoch's validation macro-F1.  `native=False` runs the same loop through MPNetm / torch.optim.Adam epoch by epoch
+    (the reference's call structure; for debugging)."""
+    if native and _native_ok(metapaths):
         return _train_candidate_native(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
                                        metapaths, epochs).last_val_f1
     _, _, f1_val = _train_candidate(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim,
@@ -290,7 +314,7 @@ def mpgnn_parallel_multiple_batch(data_mpgnn, input_dim, hidden_dim, num_rel, ou
             wave.append((i, tr))
         torch.cuda.synchronize()
         with concurrent.futures.ThreadPoolExecutor(max_workers=len(wave)) as pool:
-            futs = [pool.submit(tr.run, epochs) for _, tr in wave]
+            futs = [pool.submit(tr.run, epochs, validate_every_epoch=False) for _, tr in wave]
             for f in futs:
                 f.result()
         for i, tr in wave:
@@ -303,7 +327,7 @@ def mpgnn_parallel_multiple_x(data_mpgnn, input_dim, hidden_dim, num_rel, output
     """main.py:1136-1160 -- same for a list of metapaths; returns test macro-F1 if `testing`."""
     if isinstance(metapaths[0], (int, np.integer)):
         metapaths = [metapaths]
-    if native and len(metapaths) == 1 and 1 <= len(metapaths[0]) <= 8:
+    if native and _native_ok(metapaths):
         tr = _train_candidate_native(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, metapaths,
                                      epochs)
         test_loss, f1_test = tr.evaluate("test")

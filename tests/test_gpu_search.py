@@ -138,3 +138,64 @@ def test_k5_scorer_fb15k237_shape_with_source_mask_matches_oracle():
             ref.append(float(loss))
         assert np.allclose(traj.numpy(), ref, rtol=1e-4, atol=1e-8), (rel, traj[-3:], ref[-3:])   # the whole trajectory
         assert arg.cpu()[srcs].tolist() == cols[first[srcs]].tolist()                            # last forward's argmax
+
+
+def _unragged(flat, ptr):
+    return [flat[ptr[i]:ptr[i + 1]].tolist() for i in range(len(ptr) - 1)]
+
+
+def test_search_non_synthetic_branch_matches_reference_golden():
+    """dataset='fb15k-237' through step 0 and one whole bag iteration (main.py:1289-1355, 1381-1435): labelled source
+    list, labels aligned with the position in that list (main.py:424, 653-654), and `args.dataset` passed on to the
+    dictionaries built after the relabelling (main.py:1433).  Golden: tests/golden/search_fb_small.npz, recorded from
+    the unmodified reference on a small FB15K-237-shaped graph (make_golden_search_fb.py)."""
+    g = load_golden("search_fb_small")
+    ds = "fb15k-237"
+    x, ei, et = torch.from_numpy(g["x"]), torch.from_numpy(g["edge_index"]), torch.from_numpy(g["edge_type"])
+    labelled, labels = g["labelled"].tolist(), torch.from_numpy(g["labels"])
+    f = x.size(1)
+    data = mpgnn_b200.Data(x=x, edge_index=ei, edge_type=et, labels=labels.unsqueeze(-1), num_nodes=x.size(0),
+                           source_nodes_mask=labelled)
+    rels = search.node_types_and_connected_relations(data, BAGS=False, dataset=ds)
+    assert rels == g["actual_relations"].tolist()
+    out = [mpgnn_b200.score_relation_parallel(data, rel, data.source_nodes_mask, f, ds) for rel in rels]
+    losses = [o[1] for o in out]
+    assert np.allclose(losses, g["step0_losses"], rtol=1e-4, atol=1e-7), (losses, g["step0_losses"])
+    assert search.gap_select_step0(rels, losses) == g["step0_best"].tolist()
+    rel0 = int(g["rel0"])
+    _, _, edg, dst = out[rels.index(rel0)]
+    assert list(edg.keys()) == g["rel0_edge_keys"].tolist() and list(dst.keys()) == g["rel0_dest_keys"].tolist()
+    assert [[float(v) for v in vals] for vals in dst.values()] == _unragged(g["rel0_dest_vals"], g["rel0_dest_ptr"])
+    bag_data = search._copy_bag(data)
+    search.create_bags(edg, dst, bag_data)
+    assert bag_data.bags == [[int(v) for v in b] for b in _unragged(g["bags_flat"], g["bags_ptr"])]
+    assert bag_data.bag_labels.reshape(-1).tolist() == g["bag_labels"].tolist()
+    rels_k = search.node_types_and_connected_relations(bag_data, BAGS=True, dataset=ds)
+    assert rels_k == g["bag_relations"].tolist()
+    results, cache = [], {}
+    for rr in rels_k:
+        res = search.score_relation_bags_parallel(bag_data, rr, f, ds, metapath_len=1)
+        cache[rr] = res
+        assert bool(res[4]) == bool(g["bag_r%d_skip" % rr])
+        ref = float(g["bag_r%d_loss" % rr])
+        assert abs(res[1] - ref) <= 1e-4 * ref + 1e-7, (rr, res[1], ref)
+        if not res[4]:
+            results.append((rr, res[1]))
+    accepted = search.accept_bag_relations(results)
+    assert accepted == g["bag_accepted"].tolist()
+    for rr in accepted:
+        res = cache[rr]
+        tag = "acc_r%d_" % rr
+        assert np.allclose(res[2].output.LinearLayerAttri.weight[0].numpy(), g[tag + "lin"], atol=2e-6)
+        data_copy = search._copy_bag(bag_data)
+        preds = {k: list(v) for k, v in res[3].items()}
+        preds = search.retrain_bags(data_copy, rr, preds, True, f, ds, metapath_len=1)
+        src_mask, new_labels = search.relabel_nodes_inside_bags(preds, data_copy, res[2])
+        assert src_mask == g[tag + "src_mask"].tolist()
+        assert new_labels.reshape(-1).tolist() == g[tag + "new_labels"].tolist()
+        e2, d2 = search.create_edge_dictionary(data_copy, rr, src_mask, BAGS=False, dataset=ds)       # main.py:1433
+        e3, d3 = search.clean_dictionaries(data_copy, e2, d2, res[2])
+        assert list(e3.keys()) == g[tag + "edge_keys"].tolist()
+        assert [list(v) for v in e3.values()] == [[int(u) for u in b] for b in _unragged(g[tag + "edge_vals"], g[tag + "edge_ptr"])]
+        assert list(d3.keys()) == g[tag + "dest_keys"].tolist()
+        assert [[float(u) for u in v] for v in d3.values()] == _unragged(g[tag + "dest_vals"], g[tag + "dest_ptr"])

@@ -199,3 +199,86 @@ def test_trainer_c2_shape_trace_matches_oracle():
     assert np.allclose(trace[:, 0], ref[:, 0], rtol=1e-4)
     assert np.allclose(trace[:, 1], ref[:, 1], rtol=1e-4)
     assert np.allclose(trace[:, 2:], ref[:, 2:], atol=5e-4)
+
+
+def test_trainer_multi_metapath_matches_reference_golden(fx3):
+    """mpgnn_parallel_multiple_x (main.py:1136-1160) on the native trainer: a two-metapath model ([[1, 0], [3]],
+    embeddings concatenated, model.py:203-220) against the unmodified reference's 5-epoch dropout-free trace and
+    test result, and against the epoch-by-epoch Python path (MPNetm + torch.optim.Adam) of this repo."""
+    g = load_golden("model_len3")
+    data = _bag(fx3)
+    metas = [[1, 0], [3]]
+    ref, ref_test = g["trace5_m10_m3"], g["trace5_m10_m3_test"]
+    torch.manual_seed(30)
+    model = mpgnn_b200.MPNetm(2, 64, fx3["num_relations"], 64, 2, len(metas), metas, device="cpu")
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    traces = {}
+    for use_graph in (True, False):
+        tr = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, metas, dropout_p=0.0, max_epochs=5)
+        tr.load_state_dict(sd0)
+        got = tr.state_dict()
+        assert list(got) == list(sd0)
+        for k, v in sd0.items():
+            assert torch.equal(got[k], v), k                      # flat layout round trip incl. the [H, 2H] fc1 transpose
+        trace = tr.run(5, use_graph=use_graph)[:5]
+        traces[use_graph] = trace
+        assert np.allclose(trace[:, 0], ref[:, 0], rtol=1e-4), (trace[:, 0], ref[:, 0])
+        assert np.allclose(trace[:, 1], ref[:, 1], rtol=1e-4)
+        assert np.allclose(trace[:, 2:], ref[:, 2:], atol=2e-3)
+        loss_t, f1_t = tr.evaluate("test")
+        assert abs(loss_t - ref_test[0]) < 1e-3 * abs(ref_test[0]) and abs(f1_t - ref_test[1]) < 2e-3
+    assert np.array_equal(traces[True], traces[False])
+    # the reference-facing call takes the native path for unions too and returns the test macro-F1
+    torch.manual_seed(30)
+    f1_native = mpgnn_b200.mpgnn_parallel_multiple_x(data, 2, 64, 4, 64, 2, metas, True, epochs=5)
+    model.load_state_dict(sd0)
+    model.to("cuda")
+    model.dropout.p = model.dropout2.p = 0.0
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0005)
+    for _ in range(5):
+        mpgnn_b200.mpgnn_train(model, opt, data)
+    sd5 = tr.state_dict()
+    for k, v in model.state_dict().items():
+        assert rel_err(sd5[k], v.cpu()) < 1e-4, k
+    assert 0.0 <= f1_native <= 1.0
+
+
+def test_trainer_validate_last_returns_the_every_epoch_result(fx3):
+    """MPGNN_TRAINER_VALIDATE_LAST skips the validation passes whose results the reference discards (main.py:1134
+    returns the last epoch's): same parameters bit for bit, same returned F1, NaN where nothing was computed."""
+    g = load_golden("model_len3")
+    data = _bag(fx3)
+    out = {}
+    for every in (True, False):
+        tr = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, [1, 0], dropout_p=0.6, seed=11, max_epochs=40)
+        tr.load_state_dict(_sd(g, "sd0."))
+        trace = tr.run(40, validate_every_epoch=every)[:40]
+        out[every] = (trace, tr.last_val_f1, tr.state_dict())
+    full, last = out[True], out[False]
+    assert full[1] == last[1] == full[0][-1, 3]
+    assert np.array_equal(full[0][:, 0], last[0][:, 0])                       # same train losses
+    assert np.array_equal(full[0][-1], last[0][-1]) and np.isnan(last[0][:-1, 1:]).all()
+    for k in full[2]:
+        assert torch.equal(full[2][k], last[2][k]), k
+
+
+def test_trainer_requires_parameters_and_valid_labels(fx3):
+    data = _bag(fx3)
+    tr = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, [1, 0], dropout_p=0.0, max_epochs=3)
+    with pytest.raises(ValueError):
+        tr.run(1)                                       # no load_state_dict yet: refuse to train a recycled slab's bytes
+    bad = _bag(fx3)
+    bad.train_y = fx3["train_y"].clone()
+    bad.train_y[0] = 5
+    with pytest.raises(ValueError):
+        mpgnn_b200.CandidateTrainer(bad, 2, 64, 2, [1, 0])
+    bad2 = _bag(fx3)
+    bad2.val_idx = list(fx3["val_idx"])
+    bad2.val_idx[3] = fx3["x"].size(0) + 7
+    with pytest.raises(ValueError):
+        mpgnn_b200.CandidateTrainer(bad2, 2, 64, 2, [1, 0])
+    # a relation id the edge list never uses is an empty relation, as in the reference (edge_type == r is empty)
+    tr9 = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, [9, 0], dropout_p=0.0, max_epochs=2)
+    torch.manual_seed(30)
+    tr9.load_state_dict(mpgnn_b200.MPNetm(2, 64, 4, 64, 2, 1, [[9, 0]], device="cpu").state_dict())
+    assert np.isfinite(tr9.run(2)[:2]).all()
