@@ -34,6 +34,8 @@ extern "C" {
 #define MPGNN_F_NEED_GX 8u      /* bwd: also produce the input gradient (hidden layers)      */
 #define MPGNN_F_TF32X3 16u      /* projection on tcgen05 with the 3xTF32 split (fp32 parity) */
 #define MPGNN_F_BF16 32u        /* reserved: not built, every entry point rejects it (ENOTSUP) */
+#define MPGNN_F_COMPACT_H 64u   /* force the compact hop (d_h = one row per non-empty bucket) where the shapes allow */
+#define MPGNN_F_DENSE_H 128u    /* never use the compact hop (d_h = N rows)                                            */
 
 typedef struct mpgnn_graph mpgnn_graph; /* relation-typed CSR + CSC, device resident */
 
@@ -117,6 +119,15 @@ int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, cons
                   const uint32_t* d_actmask, const float* d_gy, int64_t f_in, const float* d_w, const float* d_root,
                   int64_t f_out, uint32_t flags, double dropout_p, float* d_gx, float* d_gw, float* d_groot,
                   float* d_gbias, void* d_workspace, int64_t workspace_bytes, void* stream);
+/* Layout of d_h.  When most buckets of the relation are empty (and the shapes are the tensor-core ones) the hop keeps
+ * the aggregated features COMPACT: d_h holds one row per node that has an edge of the relation (ascending node id), the
+ * projection runs as  y = act(x root + b + scatter(h_c W))  and the backward contracts only those rows.  The choice is a
+ * pure function of (graph, relation, f_in, f_out, flags & (TF32X3 | COMPACT_H | DENSE_H)); mpgnn_hop_fwd and
+ * mpgnn_hop_bwd must be given the same values.  Returns the number of rows of d_h the pair uses: num_nodes (dense) or
+ * the relation's number of non-empty buckets (compact); negative on error.  d_h always needs room for N x f_in. */
+int64_t mpgnn_hop_h_rows(const mpgnn_graph* g, int64_t relation, int64_t f_in, int64_t f_out, uint32_t flags);
+/* Non-empty rows of a relation, ascending (device pointer into the handle, *count of them). */
+int mpgnn_graph_relation_rows(const mpgnn_graph* g, int64_t relation, const int32_t** d_rows, int64_t* count);
 /* Scratch both hop calls need for (N, f_in, f_out). */
 int64_t mpgnn_hop_workspace_bytes(int64_t num_nodes, int64_t f_in, int64_t f_out);
 

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("MPGNN_B200_LIB") or os.path.join(HERE, "libmpgnn_b200
 
 OK, EINVAL, ECUDA, ERANGE, ENOTSUP = 0, -1, -2, -3, -4
 F_RELU, F_DROPOUT_SEED, F_DROPOUT_MASK, F_NEED_GX, F_TF32X3, F_BF16 = 1, 2, 4, 8, 16, 32
+F_COMPACT_H, F_DENSE_H = 64, 128
 
 _c = ctypes
 _i64, _i32, _u32, _u64, _dbl, _ptr = _c.c_int64, _c.c_int, _c.c_uint32, _c.c_uint64, _c.c_double, _c.c_void_p
@@ -36,6 +37,8 @@ PROTOTYPES = {
     "mpgnn_hop_bwd": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _u32, _dbl, _ptr,
                              _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "mpgnn_hop_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "mpgnn_hop_h_rows": (_i64, [_ptr, _i64, _i64, _i64, _u32]),
+    "mpgnn_graph_relation_rows": (_i32, [_ptr, _i64, _c.POINTER(_ptr), _c.POINTER(_i64)]),
     "mpgnn_gemm_rows": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _ptr, _i32, _ptr, _i64, _ptr, _i64,
                                _ptr, _i64, _ptr]),
     "mpgnn_gemm_tn": (_i32, [_ptr, _i64, _i64, _i64, _ptr, _i64, _i64, _ptr, _i64, _ptr, _ptr, _i64, _ptr]),

@@ -84,6 +84,7 @@ int graph_build_device(const int64_t* d_edge_index, const int64_t* d_edge_type, 
                        cudaStream_t s, mpgnn_graph_impl** out);
 void graph_free(mpgnn_graph_impl* g);
 int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out);
+int hop_h_compact(const mpgnn_graph_impl* g, int64_t rel, int64_t f_in, int64_t f_out, uint32_t flags);
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
             const uint8_t* mask_bits, float* h, float* y, uint32_t* actmask, void* ws_ptr, int64_t ws_bytes,
@@ -263,6 +264,24 @@ int mpgnn_hop_bwd(const mpgnn_graph* g, int64_t relation, const float* d_x, cons
                   float* d_gbias, void* d_workspace, int64_t workspace_bytes, void* stream) {
   return hop_bwd(impl(g), relation, d_x, d_h, d_y, d_actmask, d_gy, f_in, d_w, d_root, f_out, flags, dropout_p, d_gx, d_gw,
                  d_groot, d_gbias, d_workspace, workspace_bytes, stream_of(stream));
+}
+
+int64_t mpgnn_hop_h_rows(const mpgnn_graph* g, int64_t relation, int64_t f_in, int64_t f_out, uint32_t flags) {
+  const mpgnn_graph_impl* gi = impl(g);
+  MPGNN_REQUIRE(gi != nullptr, MPGNN_EINVAL, "hop_h_rows: NULL graph");
+  MPGNN_REQUIRE(relation >= 0 && relation < gi->r, MPGNN_ERANGE, "hop_h_rows: relation %lld outside [0,%lld)",
+                (long long)relation, (long long)gi->r);
+  return hop_h_compact(gi, relation, f_in, f_out, flags) ? graph_rel_nnz_rows(gi, relation) : gi->n;
+}
+
+int mpgnn_graph_relation_rows(const mpgnn_graph* g, int64_t relation, const int32_t** d_rows, int64_t* count) {
+  const mpgnn_graph_impl* gi = impl(g);
+  MPGNN_REQUIRE(gi && d_rows && count, MPGNN_EINVAL, "graph_relation_rows: NULL argument");
+  MPGNN_REQUIRE(relation >= 0 && relation < gi->r, MPGNN_ERANGE, "graph_relation_rows: relation %lld outside [0,%lld)",
+                (long long)relation, (long long)gi->r);
+  *d_rows = gi->nz_rows + gi->rel_nz_host[relation];
+  *count = graph_rel_nnz_rows(gi, relation);
+  return MPGNN_OK;
 }
 
 int64_t mpgnn_hop_workspace_bytes(int64_t num_nodes, int64_t f_in, int64_t f_out) {

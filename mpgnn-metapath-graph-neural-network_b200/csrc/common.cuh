@@ -84,6 +84,7 @@ struct HeavyRows {
   int32_t* chunk_ptr;        // [count] first chunk of the bucket, counted inside its relation               (device)
   int64_t* rel_ptr_host;     // [r+1] slice of rows / chunk_ptr belonging to each relation
   int64_t* rel_chunks_host;  // [r]   chunks in each relation
+  int32_t* rows_compact;     // [count] rank of the bucket among the non-empty buckets of its relation (CSR side only)
 };
 
 struct mpgnn_graph_impl {
@@ -96,6 +97,16 @@ struct mpgnn_graph_impl {
   int32_t* csc_idx;  // [e] target (row) of each edge
   int32_t* csc_eid;  // [e]
   int64_t* rel_offsets_host;  // [r+1] csr_ptr[k*n] copied to the host
+  // ---- compact (DCSR) view of the CSR side: with E_r << N most buckets of a relation are empty (73 % at C4), and
+  // everything the hop computes FROM the aggregated features -- h W, h^T g_z, (g_z W^T)/deg -- only exists on the
+  // rows with edges.  Rank = position of a row among the non-empty rows of its relation.
+  int64_t groups;             // G = ceil(n / 32) 32-row groups per relation
+  uint32_t* grp_bits;         // [r*G]   bit l of word (rel, g) = row 32g+l of the relation has edges
+  uint32_t* grp_rank;         // [r*G+1] exclusive prefix of popc(grp_bits) over ALL relations (subtract rel_nz_host[rel])
+  int32_t* nz_rows;           // [nz]    non-empty rows, relation after relation, ascending inside a relation
+  int32_t* cptr;              // [nz+r]  compact row pointers: relation `rel` owns entries rel_nz_host[rel]+rel .. (nnz_rel+1 of them)
+  int32_t* csc_cidx;          // [e]     like csc_idx, but the RANK of the target row (what a compact [nnz, F] matrix is indexed by)
+  int64_t* rel_nz_host;       // [r+1]   prefix of the number of non-empty rows per relation
 };
 
 // ---- internal launchers shared between translation units --------------------------------
@@ -126,6 +137,9 @@ struct GemmRowsArgs {
   // activation bitmask (tcgen05 path only): word (row, c) bit j = [out(row, 32c+j) > 0]
   uint32_t* actmask_out;                  // written by the epilogue when non-null (needs n % 32 == 0)
   const uint32_t* a1_actmask; float a1_scale;   // A1(r,k) := bit(r,k) ? A1(r,k)*a1_scale : 0 (k2 must be 0)
+  // tcgen05 path only: out(row,:) += add_src[rank(row),:] (before bias / activation) for the rows flagged in add_bits
+  // (32 rows per word); rank(row) = add_rank[row/32] - add_base + number of flagged rows below it in its word
+  const float* add_src; int64_t ld_add; const uint32_t* add_bits; const uint32_t* add_rank; uint32_t add_base;
 };
 int launch_gemm_rows(const GemmRowsArgs& a, cudaStream_t s);
 
@@ -151,12 +165,23 @@ int launch_relu_dropout_bwd(const float* gy, const float* y, float scale, float*
 int launch_pack_actmask(const float* y, int64_t m, int64_t n, uint32_t* mask, cudaStream_t s);
 int launch_relu_dropout_bwd_mask(const float* gy, const uint32_t* mask, float scale, float* gz, int64_t m, int64_t n,
                                  cudaStream_t s);
+int launch_gather_gated_rows(const float* gy, int64_t ldgy, const uint32_t* mask, float scale, const int32_t* rows,
+                             int64_t n_rows, int64_t n, float* out, cudaStream_t s);
 
 // aggregation over relation `rel` of a graph handle (transpose = CSC view), hub buckets included
 int launch_spmm_graph(const mpgnn_graph_impl* g, int64_t rel, int transpose, int mean, const float* x, int64_t ldx,
                       int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s);
 int launch_spmm(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,
                 int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s);
+// compact forms: out[k,:] = mean of the bucket of the k-th non-empty row (k < nnz_rel);
+// out[j,:] += sum_{e: col(e)=j} t_c[rank(row(e)),:] in place (t_c indexed by rank)
+int launch_spmm_graph_compact(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t ldx, int64_t feat, float* out,
+                              int64_t ldout, cudaStream_t s);
+int launch_spmm_graph_transpose_compact(const mpgnn_graph_impl* g, int64_t rel, const float* t_c, int64_t ldt, int64_t feat,
+                                        float* out, int64_t ldout, cudaStream_t s);
+static inline int64_t graph_rel_nnz_rows(const mpgnn_graph_impl* g, int64_t rel) {
+  return g->rel_nz_host[rel + 1] - g->rel_nz_host[rel];
+}
 
 // ---- device helpers ---------------------------------------------------------------------
 // Counter-based dropout randomness, stateless (the stream does not depend on the launch geometry,

@@ -505,4 +505,43 @@ int launch_relu_dropout_bwd_mask(const float* gy, const uint32_t* mask, float sc
   return MPGNN_OK;
 }
 
+// g_z restricted to a list of rows, compact: out[k,:] = gate(g_y[rows[k],:]) * scale with gate = the activation bitmask of
+// y (null = no gate).  One float4 per thread, a row's 128-bit pieces on consecutive lanes (full 512-byte rows at F = 128).
+__global__ void __launch_bounds__(256) gather_gated_rows_kernel(const float* __restrict__ gy, int64_t ldgy,
+                                                                const uint32_t* __restrict__ mask, float scale,
+                                                                const int32_t* __restrict__ rows, int64_t n_rows, int units,
+                                                                float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t work = n_rows * units;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < work; i += stride) {
+    const int64_t k = i / units;
+    const int u = (int)(i - k * units);
+    const int64_t row = __ldg(rows + k);
+    float4 v = __ldg(reinterpret_cast<const float4*>(gy + row * ldgy) + u);
+    if (mask != nullptr) {
+      const uint32_t nib = __ldg(mask + row * (units >> 3) + (u >> 3)) >> ((u & 7) * 4);
+      v.x = (nib & 1u) ? v.x * scale : 0.f;
+      v.y = (nib & 2u) ? v.y * scale : 0.f;
+      v.z = (nib & 4u) ? v.z * scale : 0.f;
+      v.w = (nib & 8u) ? v.w * scale : 0.f;
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+int launch_gather_gated_rows(const float* gy, int64_t ldgy, const uint32_t* mask, float scale, const int32_t* rows,
+                             int64_t n_rows, int64_t n, float* out, cudaStream_t s) {
+  MPGNN_REQUIRE(n % 32 == 0 && ldgy % 4 == 0, MPGNN_ENOTSUP, "gather_gated_rows: the feature width must be a multiple of 32");
+  MPGNN_REQUIRE(((uintptr_t)gy % 16 == 0) && ((uintptr_t)out % 16 == 0), MPGNN_EINVAL, "gather_gated_rows: unaligned operand");
+  const int units = (int)(n / 4);
+  const int64_t work = n_rows * units;
+  if (work <= 0) return MPGNN_OK;
+  int64_t blocks = ceil_div(work, 256);
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  gather_gated_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(gy, ldgy, mask, scale, rows, n_rows, units, out);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
 }  // namespace mpgnn

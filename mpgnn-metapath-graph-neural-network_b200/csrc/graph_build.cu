@@ -269,6 +269,7 @@ __global__ void collect_heavy_kernel(const int32_t* __restrict__ ptr, int64_t bu
 static void free_heavy(HeavyRows* h) {
   cudaFree(h->rows);
   cudaFree(h->chunk_ptr);
+  cudaFree(h->rows_compact);
   free(h->rel_ptr_host);
   free(h->rel_chunks_host);
   memset(h, 0, sizeof(*h));
@@ -335,8 +336,133 @@ static int find_heavy(const int32_t* ptr, int64_t n, int64_t r, cudaStream_t s, 
   return MPGNN_OK;
 }
 
+// ---- compact (DCSR) view of the CSR side ------------------------------------------------------------------------
+// one warp per 32-row group of a relation: which of its rows have edges
+__global__ void __launch_bounds__(256) group_bits_kernel(const int32_t* __restrict__ ptr, int64_t n, int64_t r, int64_t groups,
+                                                         uint32_t* __restrict__ bits, uint32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= r * groups) return;
+  const int64_t rel = w / groups, row = (w % groups) * 32 + lane;
+  bool nz = false;
+  if (row < n) {
+    const int64_t b = rel * n + row;
+    nz = ptr[b + 1] > ptr[b];
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, nz);
+  if (lane == 0) {
+    bits[w] = m;
+    counts[w] = (uint32_t)__popc(m);
+  }
+}
+// the non-empty rows and their row pointers, in rank order: relation `rel` owns nz_rows[base(rel) ..) and
+// cptr[base(rel) + rel ..] (one more entry than rows: the end of its last bucket)
+__global__ void __launch_bounds__(256) compact_rows_kernel(const int32_t* __restrict__ ptr, int64_t n, int64_t r, int64_t groups,
+                                                           const uint32_t* __restrict__ bits, const uint32_t* __restrict__ rank,
+                                                           int32_t* __restrict__ nz_rows, int32_t* __restrict__ cptr) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= r * groups) return;
+  const int64_t rel = w / groups, row = (w % groups) * 32 + lane;
+  const uint32_t m = bits[w];
+  if ((m >> lane) & 1u) {
+    const int64_t pos = (int64_t)rank[w] + __popc(m & ((1u << lane) - 1u));
+    nz_rows[pos] = (int32_t)row;
+    cptr[pos + rel] = ptr[rel * n + row];
+  }
+  if (w % groups == 0 && lane == 0) cptr[(int64_t)rank[w + groups] + rel] = ptr[(rel + 1) * n];   // closes the relation
+}
+// rank of the target row of every edge in CSC order (binary search of the edge's relation in the r+1 offsets)
+__global__ void __launch_bounds__(256) compact_index_kernel(const int32_t* __restrict__ csc_idx, int64_t e, int64_t r, int64_t groups,
+                                                            const int32_t* __restrict__ csc_ptr, int64_t n,
+                                                            const uint32_t* __restrict__ bits, const uint32_t* __restrict__ rank,
+                                                            int32_t* __restrict__ cidx) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= e) return;
+  int64_t lo = 0, hi = r - 1;                      // last relation whose first position is <= p
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) >> 1;
+    if ((int64_t)csc_ptr[mid * n] <= p) lo = mid; else hi = mid - 1;
+  }
+  const int32_t row = csc_idx[p];
+  const int64_t w = lo * groups + (row >> 5);
+  cidx[p] = (int32_t)(rank[w] - rank[lo * groups] + __popc(bits[w] & ((1u << (row & 31)) - 1u)));
+}
+__global__ void heavy_rank_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ rel_of, int64_t count,
+                                  int64_t groups, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ rank,
+                                  int32_t* __restrict__ rows_compact) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int64_t rel = rel_of[k];
+  const int32_t row = rows[k];
+  const int64_t w = rel * groups + (row >> 5);
+  rows_compact[k] = (int32_t)(rank[w] - rank[rel * groups] + __popc(bits[w] & ((1u << (row & 31)) - 1u)));
+}
+
+static int build_compact(mpgnn_graph_impl* g, cudaStream_t s) {
+  const int64_t n = g->n, r = g->r, e = g->e;
+  const int64_t G = ceil_div(n, 32), words = r * G;
+  g->groups = G;
+  g->rel_nz_host = static_cast<int64_t*>(calloc(r + 1, sizeof(int64_t)));
+  MPGNN_REQUIRE(g->rel_nz_host != nullptr, MPGNN_ECUDA, "graph_build: host allocation failed");
+  MPGNN_REQUIRE(words + 1 < (1LL << 31), MPGNN_ENOTSUP, "graph_build: R*N/32 does not fit the group index");
+  MPGNN_CUDA_CHECK(cudaMalloc(&g->grp_bits, (size_t)words * 4));
+  MPGNN_CUDA_CHECK(cudaMalloc(&g->grp_rank, (size_t)(words + 1) * 4));
+  const int64_t scan_bytes = exclusive_scan_tmp_bytes(words + 1);
+  void* scan_tmp = nullptr;
+  MPGNN_CUDA_CHECK(cudaMalloc(&scan_tmp, (size_t)scan_bytes));
+  MPGNN_CUDA_CHECK(cudaMemsetAsync(g->grp_rank, 0, (size_t)(words + 1) * 4, s));
+  const unsigned wb = (unsigned)ceil_div(words * 32, 256);
+  group_bits_kernel<<<wb, 256, 0, s>>>(g->csr_ptr, n, r, G, g->grp_bits, g->grp_rank);
+  MPGNN_LAUNCH_CHECK();
+  int rc = exclusive_scan_u32(g->grp_rank, g->grp_rank, words + 1, scan_tmp, scan_bytes, s);
+  std::vector<uint32_t> base(r + 1);
+  if (rc == MPGNN_OK) {
+    cudaError_t ce = cudaMemcpy2DAsync(base.data(), 4, g->grp_rank, (size_t)G * 4, 4, (size_t)(r + 1), cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) { set_error("graph_build: %s", cudaGetErrorString(ce)); rc = MPGNN_ECUDA; }
+  }
+  cudaFree(scan_tmp);
+  MPGNN_PROPAGATE(rc);
+  for (int64_t k = 0; k <= r; ++k) g->rel_nz_host[k] = base[k];
+  const int64_t nz = g->rel_nz_host[r];
+  MPGNN_CUDA_CHECK(cudaMalloc(&g->nz_rows, (size_t)(nz > 0 ? nz : 1) * 4));
+  MPGNN_CUDA_CHECK(cudaMalloc(&g->cptr, (size_t)(nz + r) * 4));
+  MPGNN_CUDA_CHECK(cudaMalloc(&g->csc_cidx, (size_t)(e > 0 ? e : 1) * 4));
+  compact_rows_kernel<<<wb, 256, 0, s>>>(g->csr_ptr, n, r, G, g->grp_bits, g->grp_rank, g->nz_rows, g->cptr);
+  MPGNN_LAUNCH_CHECK();
+  if (e > 0) {
+    compact_index_kernel<<<(unsigned)ceil_div(e, 256), 256, 0, s>>>(g->csc_idx, e, r, G, g->csc_ptr, n, g->grp_bits, g->grp_rank,
+                                                                     g->csc_cidx);
+    MPGNN_LAUNCH_CHECK();
+  }
+  HeavyRows& hv = g->heavy[0];
+  if (hv.count > 0) {
+    std::vector<int32_t> rel_of(hv.count);
+    for (int64_t rel = 0; rel < r; ++rel)
+      for (int64_t k = hv.rel_ptr_host[rel]; k < hv.rel_ptr_host[rel + 1]; ++k) rel_of[k] = (int32_t)rel;
+    int32_t* d_rel = nullptr;
+    MPGNN_CUDA_CHECK(cudaMalloc(&d_rel, (size_t)hv.count * 4));
+    MPGNN_CUDA_CHECK(cudaMalloc(&hv.rows_compact, (size_t)hv.count * 4));
+    MPGNN_CUDA_CHECK(cudaMemcpyAsync(d_rel, rel_of.data(), (size_t)hv.count * 4, cudaMemcpyHostToDevice, s));
+    heavy_rank_kernel<<<(unsigned)ceil_div(hv.count, 256), 256, 0, s>>>(hv.rows, d_rel, hv.count, G, g->grp_bits, g->grp_rank,
+                                                                        hv.rows_compact);
+    MPGNN_LAUNCH_CHECK();
+    MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(d_rel);
+  }
+  MPGNN_CUDA_CHECK(cudaStreamSynchronize(s));
+  return MPGNN_OK;
+}
+
 static void free_graph(mpgnn_graph_impl* g) {
   if (!g) return;
+  cudaFree(g->grp_bits);
+  cudaFree(g->grp_rank);
+  cudaFree(g->nz_rows);
+  cudaFree(g->cptr);
+  cudaFree(g->csc_cidx);
+  free(g->rel_nz_host);
   free_heavy(&g->heavy[0]);
   free_heavy(&g->heavy[1]);
   cudaFree(g->csr_ptr);
@@ -450,6 +576,7 @@ int graph_build_device(const int64_t* d_edge_index, const int64_t* d_edge_type, 
   free(h_ptr_samples);
   if (rc == MPGNN_OK) rc = find_heavy(g->csr_ptr, n, r, s, &g->heavy[0]);
   if (rc == MPGNN_OK) rc = find_heavy(g->csc_ptr, n, r, s, &g->heavy[1]);
+  if (rc == MPGNN_OK) rc = build_compact(g, s);
   if (rc != MPGNN_OK) {
     free_graph(g);
     return rc;

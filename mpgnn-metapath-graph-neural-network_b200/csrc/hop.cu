@@ -23,6 +23,51 @@ static int64_t fwd_ws_floats(int64_t f_in, int64_t f_out) {
   return align_up(2 * f_in * f_out, 64) + align_up(proj_tcgen05_workspace_floats(2 * f_in, f_out), 64);
 }
 
+// ---- compact hop ---------------------------------------------------------------------------------------------------
+// With E_r << N most rows of h = mean_r(x) are zero (73 % at C4).  The compact form keeps h as h_c [nnz_rows, f_in] (one
+// row per non-empty bucket, graph_build.cu) and runs everything derived from it on those rows only:
+//   forward   h_c = mean_r(x) (compact K2);  hw_c = h_c W;  y = act(x root + b + scatter(hw_c))   (epilogue add by rank)
+//   backward  gz_c = g_z[rows with edges];  g_root, g_b = x^T g_z;  g_W = h_c^T gz_c;
+//             g_x = g_z root^T;  t_c = (gz_c W^T)/deg;  g_x[j] += sum_{e: col(e)=j} t_c[rank(row(e))]
+// i.e. the all-rows contractions run at K = f_in instead of 2 f_in and the h-side ones over nnz rows instead of N:
+// ~36 % fewer MMA passes (the 3xTF32 kernels are tensor-bound) and ~12 GB less HBM traffic per hop at C4.
+constexpr int64_t kCompactMinRows = 1 << 19;     // below this the extra launches cost more than the rows save
+
+int hop_h_compact(const mpgnn_graph_impl* g, int64_t rel, int64_t f_in, int64_t f_out, uint32_t flags) {
+  if ((flags & MPGNN_F_DENSE_H) || !(flags & MPGNN_F_TF32X3) || rel < 0 || rel >= g->r) return 0;
+  const int64_t n = g->n;
+  if (f_out % 32 != 0) return 0;
+  if (!proj_tcgen05_supported(n, f_in, 0, f_out, flags) || !proj_tcgen05_supported(n, f_out, 0, f_in, flags)) return 0;
+  if (!wgrad_tcgen05_supported(n, f_in, 0, f_out, flags)) return 0;
+  if (flags & MPGNN_F_COMPACT_H) return 1;
+  return n >= kCompactMinRows && 2 * graph_rel_nnz_rows(g, rel) <= n;
+}
+
+static int hop_fwd_compact(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w,
+                           const float* root, GemmRowsArgs a, uint32_t flags, float* h_c, float* bp, float* hw_c,
+                           cudaStream_t s, bool h_precomputed) {
+  const int64_t nnz = graph_rel_nnz_rows(g, rel), f_out = a.n;
+  float* img_w = bp + align_up(2 * f_in * f_out, 64);
+  float* img_root = img_w + 2 * f_in * f_out;
+  if (!h_precomputed) {
+    ScopedTimer tm("spmm_mean_fwd", s);
+    MPGNN_PROPAGATE(launch_spmm_graph_compact(g, rel, x, f_in, f_in, h_c, f_in, s));
+  }
+  if (nnz > 0) {
+    ScopedTimer tm("proj_fwd_compact_tcgen05", s);
+    GemmRowsArgs c{};
+    c.a1 = h_c; c.lda1 = f_in; c.k1 = f_in; c.b = w; c.m = nnz; c.n = f_out; c.out = hw_c; c.ldo = f_out;
+    MPGNN_PROPAGATE(launch_proj_tcgen05_ws(c, flags, img_w, s));
+  }
+  ScopedTimer tm("proj_fwd_tcgen05", s);
+  a.a1 = x; a.lda1 = f_in; a.k1 = f_in; a.a2 = nullptr; a.lda2 = 0; a.k2 = 0;
+  a.b = root;
+  a.add_src = hw_c; a.ld_add = f_out;
+  a.add_bits = g->grp_bits + rel * g->groups; a.add_rank = g->grp_rank + rel * g->groups;
+  a.add_base = (uint32_t)g->rel_nz_host[rel];
+  return launch_proj_tcgen05_ws(a, flags, img_root, s);
+}
+
 int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out) {
   int64_t floats = 0;
   floats += fwd_ws_floats(f_in, f_out);                                // packed [W;root]
@@ -56,6 +101,22 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
   Workspace ws(ws_ptr, ws_bytes);
   float* bp = ws.take<float>(fwd_ws_floats(f_in, f_out));
   MPGNN_REQUIRE(bp != nullptr, MPGNN_EINVAL, "hop_fwd: workspace too small");
+
+  if (hop_h_compact(g, rel, f_in, f_out, flags)) {
+    float* hw_c = ws.take<float>(align_up(g->n * f_out, 64));        // the g_z slot of the backward, free during the forward
+    MPGNN_REQUIRE(hw_c != nullptr, MPGNN_EINVAL, "hop_fwd: workspace too small");
+    GemmRowsArgs a{};
+    a.m = g->n; a.n = f_out;
+    a.bias = bias;
+    a.relu = (flags & MPGNN_F_RELU) ? 1 : 0;
+    a.dropout_mode = drop_seed ? 1 : (drop_mask ? 2 : 0);
+    a.dropout_p = (float)p; a.dropout_scale = (float)(1.0 / (1.0 - p));
+    a.dropout_thr16 = dropout_threshold16(p); a.seed = seed; a.offset = offset; a.mask_bits = mask_bits;
+    a.offset_ptr = offset_ptr;
+    a.out = y; a.ldo = f_out;
+    a.actmask_out = actmask;
+    return hop_fwd_compact(g, rel, x, f_in, w, root, a, flags, h, bp, hw_c, s, h_precomputed);
+  }
 
   if (!h_precomputed) {      // the caller may hold mean_r(x) already (first layer of a model: x is a constant)
     ScopedTimer tm("spmm_mean_fwd", s);
@@ -117,6 +178,67 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
   float* bp2_img = ws.take<float>(align_up(proj_tcgen05_workspace_floats(f_out, 2 * f_in), 64));
   float* t = need_gx ? ws.take<float>(align_up(n * f_in, 64)) : nullptr;
   MPGNN_REQUIRE(gz && partials && bp2 && bp2_img && (!need_gx || t), MPGNN_EINVAL, "hop_bwd: workspace too small");
+
+  if (hop_h_compact(g, rel, f_in, f_out, flags)) {
+    // d_h holds h_c [nnz, f_in] (what hop_fwd wrote under the same flags); see the comment above hop_h_compact
+    MPGNN_REQUIRE(!(flags & MPGNN_F_RELU) || actmask != nullptr, MPGNN_EINVAL,
+                  "hop_bwd: the compact hop takes [y > 0] from d_actmask (pass the bitmask mpgnn_hop_fwd wrote)");
+    const int64_t nnz = graph_rel_nnz_rows(g, rel);
+    const float sc = drop ? (float)(1.0 / (1.0 - p)) : 1.f;
+    const uint32_t* mask = (flags & MPGNN_F_RELU) ? actmask : nullptr;
+    float* gz_c = gz;
+    if (nnz > 0) {
+      ScopedTimer tm("gather_gz_compact", s);
+      MPGNN_PROPAGATE(launch_gather_gated_rows(gy, f_out, mask, sc, g->nz_rows + g->rel_nz_host[rel], nnz, f_out, gz_c, s));
+    }
+    GemmTnArgs tn{};
+    tn.a1 = x; tn.lda1 = f_in; tn.k1 = f_in; tn.k2 = 0;
+    tn.b = gy; tn.ldb = f_out; tn.n = f_out; tn.m = n;
+    tn.out1 = groot; tn.ldo1 = f_out; tn.out_ones = gbias;
+    tn.b_actmask = mask; tn.b_scale = sc;
+    {
+      ScopedTimer tm("wgrad_tn_tcgen05", s);                          // g_root = x^T g_z, g_b = colsum g_z (all rows)
+      MPGNN_PROPAGATE(launch_wgrad_tcgen05(tn, partials, s));
+    }
+    if (nnz > 0) {
+      ScopedTimer tm("wgrad_tn_compact_tcgen05", s);                  // g_W = h_c^T gz_c (rows with edges)
+      GemmTnArgs tc{};
+      tc.a1 = h; tc.lda1 = f_in; tc.k1 = f_in; tc.k2 = 0;
+      tc.b = gz_c; tc.ldb = f_out; tc.n = f_out; tc.m = nnz;
+      tc.out1 = gw; tc.ldo1 = f_out; tc.out_ones = nullptr; tc.b_scale = 1.f;
+      MPGNN_PROPAGATE(launch_wgrad_tcgen05(tc, partials, s));
+    } else {
+      MPGNN_CUDA_CHECK(cudaMemsetAsync(gw, 0, (size_t)(f_in * f_out) * 4, s));
+    }
+    if (need_gx) {
+      float* wt = bp2;                        // W^T, root^T: [f_out, f_in] each
+      float* roott = bp2 + f_out * f_in;
+      MPGNN_PROPAGATE(launch_pack_b(wt, f_in, w, 1, f_out, f_out, f_in, s));
+      MPGNN_PROPAGATE(launch_pack_b(roott, f_in, root, 1, f_out, f_out, f_in, s));
+      {
+        ScopedTimer tm("dgrad_nt_tcgen05", s);                        // g_x = g_z root^T (all rows)
+        GemmRowsArgs a{};
+        a.a1 = gy; a.lda1 = f_out; a.k1 = f_out; a.b = roott; a.m = n; a.n = f_in;
+        a.out = gx; a.ldo = f_in;
+        a.a1_actmask = mask; a.a1_scale = sc;
+        if (mask == nullptr && sc != 1.f) return MPGNN_ENOTSUP;      // unreachable: dropout implies RELU (checked above)
+        MPGNN_PROPAGATE(launch_proj_tcgen05_ws(a, flags, bp2_img + 2 * f_out * f_in, s));
+      }
+      if (nnz > 0) {
+        {
+          ScopedTimer tm("dgrad_nt_compact_tcgen05", s);              // t_c = (gz_c W^T) / deg (rows with edges)
+          GemmRowsArgs a{};
+          a.a1 = gz_c; a.lda1 = f_out; a.k1 = f_out; a.b = wt; a.m = nnz; a.n = f_in;
+          a.deg_ptr = g->cptr + g->rel_nz_host[rel] + rel; a.deg_cols = f_in;
+          a.out = t; a.ldo = f_in;
+          MPGNN_PROPAGATE(launch_proj_tcgen05_ws(a, flags, bp2_img, s));
+        }
+        ScopedTimer tm("spmm_transpose_bwd", s);
+        MPGNN_PROPAGATE(launch_spmm_graph_transpose_compact(g, rel, t, f_in, f_in, gx, f_in, s));
+      }
+    }
+    return MPGNN_OK;
+  }
 
   // g_z = g_y * [y > 0] * 1/(1-p).  With the activation bitmask and both tensor-core kernels available
   // the gating is fused into their operand loads (g_z is never materialised); otherwise one pass writes it.

@@ -76,6 +76,9 @@ struct Params {
   int n_stages;   // TMEM A stages in use (even, <= kStages): 512 columns = acc_bufs * bn + 64 * n_stages
   int acc_bufs;   // TMEM accumulators: 2 (double buffered) or 1 (released right after the epilogue's tcgen05.ld)
   const uint32_t* a_actmask; float a_scale;    // A(r,k) := bit(r,k) ? A(r,k)*a_scale : 0 ([m][K/32] words, k2 == 0)
+  // kAdd: out(row, :) += add_src[rank(row), :] before bias/activation, for the rows flagged in add_bits (bit l of word
+  // g = row 32g+l has a compact row); rank(row) = add_rank[g] - add_base + popc(add_bits[g] & lanes below l)
+  const float* add_src; int64_t ld_add; const uint32_t* add_bits; const uint32_t* add_rank; uint32_t add_base;
 #ifdef MPGNN_TC_EXPERIMENT
   int exp;   // profiling build only (scripts/exp_variants.sh): bits switch pipeline stages off; results are WRONG
 #endif
@@ -120,7 +123,8 @@ __global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, 
 // streams and converts ITS 128 rows once, keeps HALF of the B slice (BN/2 columns) in shared memory, and the leader's
 // MMA thread issues M256 x N(BN) x K8 MMAs that read both halves -- for K = 256 (forward) this is what lets one pass
 // over A produce all 128 output columns instead of two CTAs converting the same tile for 64 columns each.
-template <int kDrop, bool kDeg, bool kMasked, bool kPair = false>
+// kAdd: the epilogue adds rows of a compact matrix (the compact hop: y = act(x root + b + scatter(h_c W))).
+template <int kDrop, bool kDeg, bool kMasked, bool kPair = false, bool kAdd = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_a1,
                                                                    const __grid_constant__ CUtensorMap tmap_a2,
                                                                    const __grid_constant__ CUtensorMap tmap_out,
@@ -321,6 +325,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       }
       uint64_t row_key = 0;
       if (kDrop == 1) row_key = dropout_row_key(launch_key, (uint64_t)row);
+      const float* add_row = nullptr;             // this thread's row of the compact addend, if it has one
+      if (kAdd) {
+        const int64_t g32 = (row0 + quarter * 32) >> 5;        // row0 and quarter*32 are multiples of 32
+        uint32_t bits = 0, rank0 = 0;
+        if (row0 + quarter * 32 < p.m) {
+          bits = __ldg(p.add_bits + g32);
+          rank0 = __ldg(p.add_rank + g32) - p.add_base;
+        }
+        if ((bits >> lane) & 1u) {
+          add_row = p.add_src + (int64_t)(rank0 + __popc(bits & ((1u << lane) - 1u))) * p.ld_add + slice * BN;
+          // pull the lines this warp will add into L2 while the tile's MMAs are still running
+          for (int cc = half; cc < n_cc; cc += 2)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(add_row + cc * kEpiCols) : "memory");
+        }
+      }
       { TC_T0(); mbar_wait(bar_tfull + 8 * buf, ph); TC_ACC(e_tfull); }
       if (TC_EXP(128)) __nanosleep(500);
       tc_fence_after();
@@ -343,6 +362,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         const int lcol0 = cc * kEpiCols;                    // column inside the slice
         const int col0 = slice * BN + lcol0;                // global output column
         const bool scale_deg = kDeg && col0 < p.deg_cols;   // deg_cols is a multiple of 32 (checked on host)
+        if (kAdd && add_row != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 av = __ldg(reinterpret_cast<const float4*>(add_row + lcol0) + q);
+            v[4 * q + 0] = __float_as_uint(__uint_as_float(v[4 * q + 0]) + av.x);
+            v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + av.y);
+            v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + av.z);
+            v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + av.w);
+          }
+        }
         float o[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -596,6 +625,7 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   p.seed = a.seed; p.offset = a.offset; p.mask_bits = a.mask_bits; p.offset_ptr = a.offset_ptr;
   p.out = a.out; p.ldo = a.ldo; p.out_split = (int)a.out_split;
   p.actmask_out = a.actmask_out; p.a_actmask = a.a1_actmask; p.a_scale = a.a1_scale;
+  p.add_src = a.add_src; p.ld_add = a.ld_add; p.add_bits = a.add_bits; p.add_rank = a.add_rank; p.add_base = a.add_base;
   // TMEM budget (512 columns): two accumulators + as many 64-column A stages as fit: six at BN = 64 (measured:
   // forward 3.81 -> 3.59 ms against four), four at BN = 128 (one accumulator + six stages was slower: 3.39 -> 3.85 ms)
   p.acc_bufs = 2;
@@ -650,6 +680,16 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
     return MPGNN_OK;
   };
   const bool deg = p.deg_ptr != nullptr && p.deg_cols > 0;
+  if (p.add_src != nullptr) {
+    MPGNN_REQUIRE(!pair && !deg && p.a_actmask == nullptr && p.add_bits != nullptr && p.add_rank != nullptr &&
+                      p.ld_add % 4 == 0 && al16(p.add_src),
+                  MPGNN_ENOTSUP, "proj_tcgen05: the compact addend goes with the plain forward epilogue only");
+    switch (p.dropout_mode) {
+      case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false, false, true>);
+      case 1: return launch(tc::gemm_rows_tc_kernel<1, false, false, false, true>);
+      default: return launch(tc::gemm_rows_tc_kernel<2, false, false, false, true>);
+    }
+  }
   if (p.a_actmask != nullptr) {
     MPGNN_REQUIRE(p.dropout_mode == 0, MPGNN_ENOTSUP, "proj_tcgen05: operand mask with a dropout epilogue");
     return deg ? launch(tc::gemm_rows_tc_kernel<0, true, true>) : launch(tc::gemm_rows_tc_kernel<0, false, true>);

@@ -342,6 +342,10 @@ __global__ void __launch_bounds__(256) spmm_heavy_finish_kernel(const int32_t* _
   }
 }
 
+static int launch_heavy(const int32_t* ptr, const int32_t* idx, const int32_t* rows, const int32_t* chunk_ptr, int n_heavy,
+                        int64_t n_chunks, int mean, const float* x, int64_t ldx, int64_t feat, const float* init, int64_t ldinit,
+                        float* out, int64_t ldout, cudaStream_t s);
+
 int launch_spmm_graph(const mpgnn_graph_impl* g, int64_t rel, int transpose, int mean, const float* x, int64_t ldx,
                       int64_t feat, const float* init, int64_t ldinit, float* out, int64_t ldout, cudaStream_t s) {
   const int32_t* ptr = (transpose ? g->csc_ptr : g->csr_ptr) + rel * g->n;
@@ -353,21 +357,56 @@ int launch_spmm_graph(const mpgnn_graph_impl* g, int64_t rel, int transpose, int
   if (h1 == h0 || !vec4)      // no hub bucket in this relation (or a layout only the general kernel takes)
     return launch_spmm_skip(ptr, idx, g->n, mean, x, ldx, feat, init, ldinit, out, ldout, 0, s);
   MPGNN_PROPAGATE(launch_spmm_skip(ptr, idx, g->n, mean, x, ldx, feat, init, ldinit, out, ldout, kHeavyDeg, s));
-  const int n_heavy = (int)(h1 - h0);
-  const int64_t n_chunks = hv.rel_chunks_host[rel];
+  return launch_heavy(ptr, idx, hv.rows + h0, hv.chunk_ptr + h0, (int)(h1 - h0), hv.rel_chunks_host[rel], mean, x, ldx, feat, init,
+                      ldinit, out, ldout, s);
+}
+
+// hub buckets of one relation through the chunked kernels; `ptr`/`rows` name the buckets in the index space `out` uses
+static int launch_heavy(const int32_t* ptr, const int32_t* idx, const int32_t* rows, const int32_t* chunk_ptr, int n_heavy,
+                        int64_t n_chunks, int mean, const float* x, int64_t ldx, int64_t feat, const float* init, int64_t ldinit,
+                        float* out, int64_t ldout, cudaStream_t s) {
   const int units = (int)(feat / 4);
   float* partial = nullptr;
   MPGNN_CUDA_CHECK(cudaMallocAsync(&partial, (size_t)n_chunks * feat * sizeof(float), s));   // stream ordered, hub relations only
   int64_t blocks = ceil_div(n_chunks, 8);
   if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
-  spmm_heavy_chunk_kernel<<<(unsigned)blocks, 256, 0, s>>>(ptr, idx, hv.rows + h0, hv.chunk_ptr + h0, n_heavy, n_chunks, x, ldx,
-                                                           units, partial);
+  spmm_heavy_chunk_kernel<<<(unsigned)blocks, 256, 0, s>>>(ptr, idx, rows, chunk_ptr, n_heavy, n_chunks, x, ldx, units, partial);
   MPGNN_LAUNCH_CHECK();
-  spmm_heavy_finish_kernel<<<(unsigned)ceil_div(n_heavy, 8), 256, 0, s>>>(ptr, hv.rows + h0, hv.chunk_ptr + h0, n_heavy, mean, units,
-                                                                          partial, init, ldinit, out, ldout);
+  spmm_heavy_finish_kernel<<<(unsigned)ceil_div(n_heavy, 8), 256, 0, s>>>(ptr, rows, chunk_ptr, n_heavy, mean, units, partial, init,
+                                                                          ldinit, out, ldout);
   MPGNN_LAUNCH_CHECK();
   MPGNN_CUDA_CHECK(cudaFreeAsync(partial, s));
   return MPGNN_OK;
+}
+
+// K2 on the compact (DCSR) view: row k of `out` ([nnz_rel, feat]) = mean over the bucket of the relation's k-th non-empty
+// row -- the same per-bucket sums in the same order as the dense form, without the 73 % (C4) of all-zero rows.
+int launch_spmm_graph_compact(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t ldx, int64_t feat, float* out,
+                              int64_t ldout, cudaStream_t s) {
+  const int64_t nnz = graph_rel_nnz_rows(g, rel);
+  if (nnz == 0) return MPGNN_OK;
+  const int32_t* ptr = g->cptr + g->rel_nz_host[rel] + rel;
+  const HeavyRows& hv = g->heavy[0];
+  const int64_t h0 = hv.count > 0 ? hv.rel_ptr_host[rel] : 0, h1 = hv.count > 0 ? hv.rel_ptr_host[rel + 1] : 0;
+  const bool vec4 = feat % 4 == 0 && ldx % 4 == 0 && ldout % 4 == 0 && aligned_to(x, 16) && aligned_to(out, 16);
+  if (h1 == h0 || !vec4) return launch_spmm_skip(ptr, g->csr_idx, nnz, 1, x, ldx, feat, nullptr, 0, out, ldout, 0, s);
+  MPGNN_PROPAGATE(launch_spmm_skip(ptr, g->csr_idx, nnz, 1, x, ldx, feat, nullptr, 0, out, ldout, kHeavyDeg, s));
+  return launch_heavy(ptr, g->csr_idx, hv.rows_compact + h0, hv.chunk_ptr + h0, (int)(h1 - h0), hv.rel_chunks_host[rel], 1, x, ldx,
+                      feat, nullptr, 0, out, ldout, s);
+}
+
+// K2^T with a compact operand: out[j,:] += sum_{e in E_r, col(e) = j} t_c[rank(row(e)),:], in place; the buckets are the CSC
+// ones (dense over the nodes), only the gathered matrix is indexed by rank (csc_cidx).
+int launch_spmm_graph_transpose_compact(const mpgnn_graph_impl* g, int64_t rel, const float* t_c, int64_t ldt, int64_t feat,
+                                        float* out, int64_t ldout, cudaStream_t s) {
+  const int32_t* ptr = g->csc_ptr + rel * g->n;
+  const HeavyRows& hv = g->heavy[1];
+  const int64_t h0 = hv.count > 0 ? hv.rel_ptr_host[rel] : 0, h1 = hv.count > 0 ? hv.rel_ptr_host[rel + 1] : 0;
+  const bool vec4 = feat % 4 == 0 && ldt % 4 == 0 && ldout % 4 == 0 && aligned_to(t_c, 16) && aligned_to(out, 16);
+  if (h1 == h0 || !vec4) return launch_spmm_skip(ptr, g->csc_cidx, g->n, 0, t_c, ldt, feat, out, ldout, out, ldout, 0, s);
+  MPGNN_PROPAGATE(launch_spmm_skip(ptr, g->csc_cidx, g->n, 0, t_c, ldt, feat, out, ldout, out, ldout, kHeavyDeg, s));
+  return launch_heavy(ptr, g->csc_cidx, hv.rows + h0, hv.chunk_ptr + h0, (int)(h1 - h0), hv.rel_chunks_host[rel], 0, t_c, ldt, feat,
+                      out, ldout, out, ldout, s);
 }
 
 static int launch_spmm_skip(const int32_t* ptr, const int32_t* idx, int64_t n_rows, int mean, const float* x, int64_t ldx,

@@ -85,9 +85,13 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t sbo) {
 
 // N = width of B (64 or 128); kMasked: B is gated by the activation bitmask; kStacked: A1, A2 are 64 wide and share
 // one 128-wide operand tile / one accumulator
-template <int N, bool kMasked, bool kStacked>
+// kSingle (swapped roles only): ONE 128-wide A operand (the compact hop: x^T g_z over all rows, h_c^T g_z over the rows
+// with edges) -- the N operand is 128 wide, half the tile, half the MMA work
+template <int N, bool kMasked, bool kStacked, bool kSingle = false>
 __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p) {
   constexpr bool kSwap = (N == 128) && !kStacked;      // g_z^T as the M operand, [h | x] as one N = 256 operand
+  static_assert(!kSingle || kSwap, "single-operand variant exists for the swapped 128-wide shape only");
+  constexpr int kHxWidth = kSingle ? kFeat : 2 * kFeat;   // width of the [h | x] (or lone) N operand
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b_tile_bytes = kRowsPerChunk * N * 4;                    // one of hi / lo
   const int stage_bytes = 4 * kATileBytes + 2 * b_tile_bytes;        // a1 hi/lo, a2 hi/lo, b hi/lo
@@ -138,12 +142,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
     for (int u = 0; u < 2; ++u) {
       a_row[u] = warp * 2 + u;
       a_col[u] = lane * 4;
-      a_soff[u] = (int)mn_tile_offset16(lane, a_row[u], kSwap ? 2 * kFeat / 32 : kFeat / 32);
+      a_soff[u] = (int)mn_tile_offset16(lane, a_row[u], kSwap ? kHxWidth / 32 : kFeat / 32);
     }
     // swapped roles: one [h | x] tile of 8 MN atoms (hi @0, lo @32K); x goes to atoms 4-7 = 16-byte units 32..63
     int a2_soff[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) a2_soff[u] = kSwap ? (int)mn_tile_offset16(lane + 32, a_row[u], 2 * kFeat / 32) : a_soff[u];
+    for (int u = 0; u < 2; ++u) a2_soff[u] = (kSwap && !kSingle) ? (int)mn_tile_offset16(lane + 32, a_row[u], 2 * kFeat / 32) : a_soff[u];
     int b_row[2], b_col[2], b_soff[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
           dst[2 + u] = z;
         } else {
           dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a1 + ra * p.lda1 + a_col[u])) : z;
-          dst[2 + u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
+          dst[2 + u] = (ok && !kSingle) ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
         }
         const int64_t rb = row0 + b_row[u];
         dst[4 + u] = (u < n_units_b && rb < r_end) ? __ldg(reinterpret_cast<const float4*>(p.b + rb * p.ldb + b_col[u])) : z;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
       for (int u = 0; u < 2; ++u) {
         if (kSwap) {
           split_store(st + a_soff[u], 2 * kATileBytes, src[u]);                    // [h | x] tile: hi @0, lo @32K
-          split_store(st + a2_soff[u], 2 * kATileBytes, src[2 + u]);
+          if (!kSingle) split_store(st + a2_soff[u], 2 * kATileBytes, src[2 + u]);
         } else {
           split_store(st + a_soff[u], kATileBytes, src[u]);                        // a1: hi @0, lo @16K
           if (!kStacked) split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
@@ -261,11 +265,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
 #endif
           // one MMA consumes K = 8 node rows = two groups of 4 K-rows
           if (kSwap) {
-            const uint32_t hx_sbo = (2 * kFeat / 32) * 512;
+            const uint32_t hx_sbo = (kHxWidth / 32) * 512;
             const uint32_t go = kg * 2 * b_sbo, ho = kg * 2 * hx_sbo;
             const uint64_t gh = desc_mn(st + 4 * kATileBytes + go, b_sbo), gl = desc_mn(st + 4 * kATileBytes + b_tile_bytes + go, b_sbo);
             const uint64_t hh = desc_mn(st + ho, hx_sbo), hl = desc_mn(st + 2 * kATileBytes + ho, hx_sbo);
-            const uint32_t idesc_t = make_idesc_mn(N, 2 * kFeat);
+            const uint32_t idesc_t = make_idesc_mn(N, kHxWidth);
             const uint32_t acc_t = (it | kg) != 0 ? 1u : 0u;
             umma_tf32(tmem_base, gh, hh, idesc_t, acc_t);
             umma_tf32(tmem_base, gl, hh, idesc_t, 1u);
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
       tc_fence_after();
     }
     if (kSwap) {      // D^T: lane = output column n, TMEM column j = row of [g_W ; g_root]
-      for (int cc = 0; cc < 2 * kFeat / 32; ++cc) {
+      for (int cc = 0; cc < kHxWidth / 32; ++cc) {
         uint32_t v[32];
         if (n_chunks > 0) {
           tmem_ld32(tmem_base + (uint32_t)(cc * 32) + ((uint32_t)(ew * 32) << 16), v);
@@ -361,7 +365,8 @@ __global__ void __launch_bounds__(32 * kRedSeg) wgrad_reduce_kernel(const float*
   const int c0 = (int)((int64_t)grid * seg / kRedSeg), c1 = (int)((int64_t)grid * (seg + 1) / kRedSeg);
   float s = 0.f;
   if (i < per) {
-    for (int c = c0; c < c1; ++c) s += partials[(int64_t)c * stride + i];
+    if (i < feat * n || out2 != nullptr)           // the second half is neither produced nor wanted without A2
+      for (int c = c0; c < c1; ++c) s += partials[(int64_t)c * stride + i];
   } else if (i < per + n && colsum != nullptr) {
     const int col = i - per;
     for (int c = c0; c < c1; ++c)
@@ -392,6 +397,7 @@ int wgrad_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32
   if (!(flags & MPGNN_F_TF32X3)) return 0;
   if (m < 1 || !(n == 64 || n == 128)) return 0;
   if (k1 == tcw::kFeat / 2 && k2 == 0) return 1;          // one 64-wide operand (head layer): stacked tile, second half zero
+  if (k1 == tcw::kFeat && k2 == 0) return n == 128;       // one 128-wide operand (compact hop): swapped roles, N operand 128
   return k1 == k2 && (k1 == tcw::kFeat || k1 == tcw::kFeat / 2);
 }
 
@@ -441,9 +447,13 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   };
   const bool masked = a.b_actmask != nullptr;
   const bool stacked = a.k1 == tcw::kFeat / 2;
+  const bool single = a.k1 == tcw::kFeat && a.k2 == 0;
   // MPGNN_WGRAD_TMA=1: the experimental TMA-fed kernel for the 128-wide layers (wgrad_tma_tcgen05.cu), for A/B runs
   static const bool use_tma = getenv("MPGNN_WGRAD_TMA") != nullptr;
-  if (use_tma && wgrad_tma_supported(a.m, a.k1, a.k2, a.n))
+  if (single) {
+    if (masked) MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, false, true>));
+    else MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, false, true>));
+  } else if (use_tma && wgrad_tma_supported(a.m, a.k1, a.k2, a.n))
     MPGNN_PROPAGATE(launch_wgrad_tma(a, grid, p.partials, 2 * tcw::kFeat * a.n, p.colsum_part, tcw::kRowsPerChunk * a.n, s));
   else
   switch ((a.n == 128 ? 4 : 0) + (masked ? 2 : 0) + (stacked ? 1 : 0)) {

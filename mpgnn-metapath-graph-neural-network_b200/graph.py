@@ -23,10 +23,8 @@ class RelationGraph:
             raise AssertionError("edge_type is required")  # reference: assert edge_type is not None (:195)
         if edge_type.numel() != edge_index.size(1):
             raise ValueError("edge_type must have one entry per edge")
-        in_data = int(edge_type.max().item()) + 1 if edge_type.numel() else 1
-        # a relation id above every id in the data has no edges (reference: `edge_type == relation` is an empty mask,
-        # mp_rgcn_layer.py:231); ids the data does hold always get their bucket
-        num_relations = in_data if num_relations is None else max(int(num_relations), in_data)
+        if num_relations is None:
+            num_relations = int(edge_type.max().item()) + 1 if edge_type.numel() else 1
         self.num_nodes, self.num_relations = int(num_nodes), int(num_relations)
         self.num_edges = int(edge_index.size(1))
         handle = ctypes.c_void_p()
@@ -113,7 +111,8 @@ def graph_for(edge_index, edge_type, num_nodes, device, num_relations=None):
             return g
     # num_relations from the caller when it knows it (main() does: tot_rel), else from the data.  A relation id the
     # edge list never uses simply has no edges (mp_rgcn_layer.py:231: an empty mask), see RelationGraph.covers().
-    g = RelationGraph(edge_index, edge_type, num_nodes, num_relations, device)
+    in_data = int(edge_type.max().item()) + 1 if edge_type.numel() else 1
+    g = RelationGraph(edge_index, edge_type, num_nodes, max(in_data, int(num_relations or 0)), device)
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (weakref.ref(edge_index), weakref.ref(edge_type), g)

@@ -170,11 +170,13 @@ class CustomRGCNConv(torch.nn.Module):
 
     # -- internal: one hop with the epilogue MPNetm wants fused ---------------------------
     def hop(self, relation, x, graph, relu=False, dropout_p=0.0, dropout_mask=None, seed=None, offset=0,
-            precision=None):
+            precision=None, h_layout="auto"):
         """`precision`: "tf32x3" (default, `self.precision`) = projection and weight gradient on tcgen05 with the
         error-compensated 3xTF32 split (fp32-class, <= 2e-6 measured) wherever the shape is eligible, the exact-fp32
         SIMT kernels otherwise; "fp32" = the SIMT kernels always."""
         precision = self.precision if precision is None else precision
+        # h_layout: "auto" = compact (one row of aggregated features per node with edges of the relation) on large sparse
+        # relations, dense otherwise; "compact" / "dense" force it where the shapes allow (tests, benchmarks)
         if not self.weight.is_cuda:
             raise RuntimeError("CustomRGCNConv has no CPU path: move the module to a CUDA device")
         if self.root is None:
@@ -198,6 +200,9 @@ class CustomRGCNConv(torch.nn.Module):
             raise NotImplementedError("precision='bf16' is not built (MPGNN_F_BF16 is rejected by the library)")
         elif precision != "fp32":
             raise ValueError("precision must be 'fp32' or 'tf32x3'")
+        if h_layout not in ("auto", "compact", "dense"):
+            raise ValueError("h_layout must be 'auto', 'compact' or 'dense'")
+        flags |= {"auto": 0, "compact": _lib.F_COMPACT_H, "dense": _lib.F_DENSE_H}[h_layout]
         if (flags & (_lib.F_DROPOUT_MASK | _lib.F_DROPOUT_SEED)) and not relu:
             raise NotImplementedError("dropout without relu is not built (MPNetm always applies relu first, "
                                       "model.py:210-214)")

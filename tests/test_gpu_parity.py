@@ -281,17 +281,25 @@ def _sd(g, prefix):
     return {k[len(prefix):]: torch.from_numpy(v) for k, v in g.items() if k.startswith(prefix)}
 
 
-def _model_from(sd, metapaths):
-    m = mpgnn_b200.MPNetm(2, 64, 4, 64, 2, len(metapaths), metapaths, device=DEV)
+def _model_from(sd, metapaths, precision="tf32x3"):
+    m = mpgnn_b200.MPNetm(2, 64, 4, 64, 2, len(metapaths), metapaths, device=DEV, precision=precision)
     m.load_state_dict({k: v.to(DEV) for k, v in sd.items()})
     return m
 
 
-def test_model_eval_and_train_step_match_reference_golden(fx3):
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_model_eval_and_train_step_match_reference_golden(fx3, precision):
+    """Both projection paths against the reference's recorded forward, loss, gradients and first Adam step.  Logits and
+    loss meet the 1e-5 bar on both.  Gradients: the exact-fp32 path (same summation orders as torch) meets 5e-5; on the
+    3xTF32 path the conv-layer gradients are held to 1e-3 -- with 5000 x 64 pre-activations per layer a handful lie
+    within rounding of zero, an fp32-accurate product may put them on the other side of the relu than torch did, and
+    each such unit moves its node's share (~1/3600 of the loss) of every gradient upstream of it; the head's gradients
+    do not pass through that gate and stay at 5e-5.  (test_gpu_tcgen05.py compares the two paths' backward at 1e-5 on
+    identical saved activations.)"""
     g = load_golden("model_len3")
     data = mpgnn_b200.Data(**{k: fx3[k] for k in ("x", "edge_index", "edge_type", "train_idx", "train_y", "val_idx",
                                                    "val_y", "test_idx", "test_y")}, num_nodes=fx3["x"].size(0))
-    model = _model_from(_sd(g, "sd0."), [[1, 0]])
+    model = _model_from(_sd(g, "sd0."), [[1, 0]], precision)
     model.eval()
     with torch.no_grad():
         logp = model(fx3["x"], fx3["edge_index"], fx3["edge_type"])
@@ -302,9 +310,12 @@ def test_model_eval_and_train_step_match_reference_golden(fx3):
     opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0005)
     loss, _ = mpgnn_b200.mpgnn_train(model, opt, data)
     assert abs(loss - float(g["step_loss"])) < FP32_TOL * abs(float(g["step_loss"]))
+    errs = {k: rel_err(p.grad, g["step_grad." + k]) for k, p in model.named_parameters()}
+    print(precision, {k: "%.1e" % v for k, v in errs.items()})
     for k, p in model.named_parameters():
-        assert rel_err(p.grad, g["step_grad." + k]) < 5 * FP32_TOL, k
-        assert rel_err(p.detach(), g["sd1." + k]) < FP32_TOL, k
+        tol = 1e-3 if (precision == "tf32x3" and k.startswith("layers_list")) else 5 * FP32_TOL
+        assert errs[k] < tol, (k, errs[k])
+        assert rel_err(p.detach(), g["sd1." + k]) < (FP32_TOL if precision == "fp32" else 1e-4), k
     model.inject_dropout_masks(None)
     f1_tr, f1_va, _, loss_val = mpgnn_b200.mpgnn_validation(model, data, None)
     assert abs(f1_tr - g["step_val"][0]) < 2e-3 and abs(f1_va - g["step_val"][1]) < 2e-3

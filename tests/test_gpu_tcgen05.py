@@ -158,9 +158,13 @@ def test_hop_tf32x3_seeded_dropout_same_stream_as_fp32():
     conv = mpgnn_b200.CustomRGCNConv(f, f, 1, flow="target_to_source", device=DEV)
     x = torch.randn(n, f, device=DEV)
     with torch.no_grad():
-        a = conv.hop(0, x, graph, dropout_p=0.6, seed=77, offset=3, precision="fp32")
-        b = conv.hop(0, x, graph, dropout_p=0.6, seed=77, offset=3, precision="tf32x3")
-    assert torch.equal(a != 0, b != 0)          # same keep decisions from the counter RNG
+        a = conv.hop(0, x, graph, relu=True, dropout_p=0.6, seed=77, offset=3, precision="fp32")
+        b = conv.hop(0, x, graph, relu=True, dropout_p=0.6, seed=77, offset=3, precision="tf32x3")
+        z = conv.hop(0, x, graph, precision="fp32")
+    # same keep decisions from the counter RNG (a pre-activation within rounding of zero may take either side of the relu)
+    sure = z.abs() > 1e-5
+    assert torch.equal((a != 0) & sure, (b != 0) & sure)
+    assert 0.35 < float((a != 0).float().mean()) / float((z > 0).float().mean()) < 0.45      # p = 0.6 dropped
     assert rel_err(b, a) < TOL
 
 
@@ -375,3 +379,115 @@ def test_bf16_flag_and_dropout_without_relu_are_rejected():
         conv.hop(0, x, graph, relu=False, dropout_p=0.5)
     with pytest.raises(NotImplementedError):
         conv.hop(0, x, graph, relu=True, precision="bf16")
+
+
+# ---- compact hop (h kept as one row per non-empty bucket) ----------------------------------------------------------
+def _sparse_graph(n, r, seed, hub=True):
+    """~0.3 edges per (relation, node) like C4, plus (hub) one target with 700 and one source with 900 edges of relation 1."""
+    g = torch.Generator().manual_seed(seed)
+    e = int(0.3 * n * r)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    et = torch.randint(0, r, (e,), generator=g)
+    if hub:
+        a = torch.randint(0, n, (700,), generator=g)
+        b = torch.randint(0, n, (900,), generator=g)
+        ei = torch.cat([ei, torch.stack([torch.full((700,), 17), a]), torch.stack([b, torch.full((900,), 23)])], 1)
+        et = torch.cat([et, torch.ones(1600, dtype=torch.long)])
+    return ei, et
+
+
+def _relation_rows(graph, rel):
+    import ctypes
+    lib = _lib.load()
+    p, cnt = ctypes.c_void_p(), ctypes.c_int64()
+    _lib.check(lib.mpgnn_graph_relation_rows(graph.handle, rel, ctypes.byref(p), ctypes.byref(cnt)))
+    from mpgnn_b200.graph import _device_view
+    return _device_view(p.value, cnt.value, graph.device).clone().long()
+
+
+@pytest.mark.parametrize("n,f_in,f_out,rel", [(40000, 128, 128, 1), (40000, 128, 128, 0), (25000, 64, 64, 1), (30001, 64, 128, 2),
+                                              (6000, 128, 128, 3)])
+def test_compact_hop_matches_dense_hop_and_oracle(n, f_in, f_out, rel):
+    from mpgnn_b200.mp_rgcn_layer import pack_mask_bits
+    lib = _lib.load()
+    ei, et = _sparse_graph(n, 4, seed=n + rel)
+    if rel == 3:                                  # a relation without any edge
+        et = et.clamp(max=2)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 4, device=DEV)
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(n, f_in, generator=gen)
+    gy = torch.randn(n, f_out, generator=gen).to(DEV)
+    mask = (torch.rand(n, f_out, generator=gen) > 0.6).float()
+    torch.manual_seed(n)
+    p = orc.conv_init(f_in, f_out)
+    w, root = p["weight"], p["root"]
+    b = torch.randn(f_out, generator=gen) * 0.1
+    xd, wd, rd, bd = x.to(DEV), w.to(DEV), root.to(DEV), b.to(DEV)
+    bits = pack_mask_bits(mask.to(DEV))
+    base = _lib.F_RELU | _lib.F_DROPOUT_MASK | _lib.F_TF32X3
+    rows = _relation_rows(graph, rel)
+    nnz = rows.numel()
+    assert nnz == torch.unique(ei[0][et == rel]).numel() and torch.equal(rows.cpu(), torch.unique(ei[0][et == rel]))
+    assert lib.mpgnn_hop_h_rows(graph.handle, rel, f_in, f_out, base | _lib.F_COMPACT_H) == nnz
+    assert lib.mpgnn_hop_h_rows(graph.handle, rel, f_in, f_out, base | _lib.F_DENSE_H) == n
+    assert lib.mpgnn_hop_h_rows(graph.handle, rel, f_in, f_out, base) == n        # small graph: the dense form by default
+    am_d = torch.empty(n, f_out // 32, dtype=torch.int32, device=DEV)
+    am_c = torch.empty_like(am_d)
+    h_d, y_d = _fwd(graph, rel, xd, wd, rd, bd, base | _lib.F_DENSE_H, bits, am_d)
+    h_c, y_c = _fwd(graph, rel, xd, wd, rd, bd, base | _lib.F_COMPACT_H, bits, am_c)
+    assert torch.equal(h_c[:nnz], h_d[rows])                          # same per-bucket sums in the same order, bit for bit
+    z, _, _ = orc.conv_forward(x, ei, et, rel, w, root, b)
+    y_ref = torch.relu(z) * mask * 2.5
+    assert rel_err(y_c, y_ref) <= TOL and rel_err(y_c, y_d) <= TOL
+    sure = (z.abs() > 1e-4).to(DEV)
+    assert torch.equal(_unpack_actmask(am_c, f_out) & sure, _unpack_actmask(am_d, f_out) & sure)
+    # backward on identical saved tensors (the dense forward's bitmask): compact vs dense
+    out_d = _bwd(graph, rel, xd, h_d, None, gy, wd, rd, base | _lib.F_DENSE_H, am_d)
+    hc_buf = torch.full_like(h_d, float("nan"))                       # only the first nnz rows may be read
+    hc_buf[:nnz] = h_c[:nnz]
+    out_c = _bwd(graph, rel, xd, hc_buf, None, gy, wd, rd, base | _lib.F_COMPACT_H, am_d, ws_fill=0xFF)
+    for name, a, c in zip(("gx", "gw", "groot", "gbias"), out_d, out_c):
+        assert torch.isfinite(c).all(), name
+        assert rel_err(c, a) <= TOL, (name, rel_err(c, a))
+    # and against the oracle's autograd-equivalent backward
+    gz = gy.cpu() * _unpack_actmask(am_d, f_out).cpu() * 2.5
+    _, h_o, cnt = orc.conv_forward(x, ei, et, rel, w, root, b)
+    ref = orc.conv_backward(x, ei, et, rel, w, root, h_o, cnt, gz)
+    for name, a, c in zip(("gx", "gw", "groot", "gbias"), ref, out_c):
+        assert rel_err(c, a) <= TOL, (name, rel_err(c, a))
+
+
+def test_compact_hop_kernel_classes_and_autograd_path():
+    """The compact form through the Python autograd function (flags carried from forward to backward) and the kernel
+    classes it launches; shapes whose weight gradient has no single-operand tensor-core form stay dense."""
+    n, f = 20000, 128
+    ei, et = _sparse_graph(n, 4, seed=5, hub=False)
+    graph = mpgnn_b200.RelationGraph(ei, et, n, 4, device=DEV)
+    torch.manual_seed(1)
+    conv = mpgnn_b200.CustomRGCNConv(f, f, 1, flow="target_to_source", device=DEV)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(2))
+    xi = x.to(DEV).requires_grad_(True)
+    gy = torch.randn(n, f, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    out = {}
+
+    def run():
+        y = conv.hop(2, xi, graph, relu=True, h_layout="compact")
+        y.backward(gy)
+        out["y"] = y.detach()
+
+    classes = _classes_of(run)
+    want = {"spmm_mean_fwd", "proj_fwd_compact_tcgen05", "proj_fwd_tcgen05", "gather_gz_compact", "wgrad_tn_tcgen05",
+            "wgrad_tn_compact_tcgen05", "dgrad_nt_tcgen05", "dgrad_nt_compact_tcgen05", "spmm_transpose_bwd"}
+    assert want <= classes and not any(c.endswith("_simt") for c in classes), sorted(classes)
+    grads_c = [xi.grad.clone(), conv.weight.grad.clone(), conv.root.grad.clone(), conv.bias.grad.clone()]
+    xi.grad = None
+    conv.zero_grad()
+    y = conv.hop(2, xi, graph, relu=True, h_layout="dense")
+    y.backward(gy)
+    assert rel_err(out["y"], y) <= TOL
+    for a, c in zip([xi.grad, conv.weight.grad, conv.root.grad, conv.bias.grad], grads_c):
+        assert rel_err(c, a) <= 5 * TOL                      # two forwards: a relu within rounding of zero may differ
+    lib = _lib.load()
+    assert lib.mpgnn_hop_h_rows(graph.handle, 2, 128, 64, _lib.F_TF32X3 | _lib.F_COMPACT_H) == n      # no such wgrad shape
+    assert lib.mpgnn_hop_h_rows(graph.handle, 2, 96, 128, _lib.F_TF32X3 | _lib.F_COMPACT_H) == n
+    assert lib.mpgnn_hop_h_rows(graph.handle, 2, 128, 128, _lib.F_COMPACT_H) == n                     # fp32 (SIMT) path
