@@ -1,10 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- dependency stand-ins that let the UNMODIFIED reference
 sources under /root/reference be imported in this container.
 
-Only `tests/golden/make_golden.py` and the `-m "not gpu"` validation tests (which skip
-when /root/reference is absent) may use this module.  Nothing on the product path, in
-`bench.py` or in the `-m gpu` tests imports it: /root/reference does not exist on the
-GPU box.
+Users: `tests/golden/make_golden*.py`, the `-m "not gpu"` validation tests (which skip when
+/root/reference is absent) and `bench.py`'s CPU legs (`--impl reference`, `cpu_baseline`), which
+run the UNMODIFIED sources vendored into `oracle/_ref/` by `oracle/build_ref.py` as the timed
+reference arm.  Nothing on the product path or in the `-m gpu` tests imports it.
 
 The reference needs torch_geometric 2.3.1 / torch_scatter / torch_sparse / mpi4py /
 seaborn / mlxtend / imblearn / matplotlib (reference requirements.txt:1-8 and
@@ -28,10 +28,21 @@ import types
 import torch
 
 REFERENCE_ROOT = os.environ.get("MPGNN_REFERENCE_ROOT", "/root/reference")
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py
 
 
 def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "mp_rgcn_layer.py"))
+
+
+def use_vendored():
+    """Point the stand-ins at oracle/_ref (the unmodified hot-path sources copied there by oracle/build_ref.py) -- the
+    form in which the reference reaches the GPU box.  Returns False when the folder is absent."""
+    global REFERENCE_ROOT
+    if not os.path.isfile(os.path.join(VENDORED_ROOT, "mp_rgcn_layer.py")):
+        return False
+    REFERENCE_ROOT = VENDORED_ROOT
+    return True
 
 
 class _Data:

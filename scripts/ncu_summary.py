@@ -47,5 +47,30 @@ if len(rows) > 2:
                 i = hdr.index(w)
                 out.append("- %s = %s %s" % (w, r[i], units[i]))
         out.append("")
+# kernel class of each captured launch: the hop launches its kernels in a fixed order (hop.cu); compact form first
+ORDER_COMPACT = ["spmm_mean_fwd", "proj_fwd_compact_tcgen05", "proj_fwd_tcgen05", "gather_gz_compact", "wgrad_tn_tcgen05",
+                 "wgrad_tn_compact_tcgen05", "dgrad_nt_tcgen05", "dgrad_nt_compact_tcgen05", "spmm_transpose_bwd"]
+ORDER_DENSE = ["spmm_mean_fwd", "proj_fwd_tcgen05", "wgrad_tn_tcgen05", "dgrad_nt_tcgen05", "spmm_transpose_bwd"]
+if len(rows) > 2:
+    import json
+    caps = rows[2:]
+    order = ORDER_COMPACT if len(caps) >= len(ORDER_COMPACT) else ORDER_DENSE
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+
+    def to_bytes(v, unit):
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+    kernels = {}
+    for cls, r in zip(order, caps):
+        kernels[cls] = {"kernel": r[hdr.index("Kernel Name")].split("(")[0][:80],
+                        "dram_bytes_read": to_bytes(r[ir], units[ir]), "dram_bytes_write": to_bytes(r[iw], units[iw]),
+                        "dram_bytes": to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]),
+                        "gpu_time_duration": "%s %s" % (r[it], units[it])}
+    json.dump({"source": "profiles/%s_ncu.md (ncu --set full --clock-control none, one hop of `bench.py %s`)" % (tag, " ".join(sys.argv[2:])),
+               "kernels": kernels}, open("profiles/r02_traffic.json" if tag.startswith("r02") else "profiles/%s_traffic.json" % tag, "w"), indent=1)
+    out += ["", "## DRAM traffic per launch and kernel class (feeds bench.py's roofline.traffic)", "",
+            "| class | kernel | read GB | write GB |", "|---|---|---:|---:|"]
+    for cls, v in kernels.items():
+        out.append("| %s | `%s` | %.3f | %.3f |" % (cls, v["kernel"], v["dram_bytes_read"] / 1e9, v["dram_bytes_write"] / 1e9))
 open("profiles/%s_ncu.md" % tag, "w").write("\n".join(out) + "\n")
 print("\n".join(out[-40:]))
