@@ -87,6 +87,13 @@ int mpgnn_graph_relation_counts(const mpgnn_graph* g, int64_t* h_counts);
 int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, const float* d_x, int64_t ldx,
                int64_t feat, const float* d_init, int64_t ldinit, float* d_out, int64_t ldout, void* stream);
 
+/* d_out[i,:] = d_x[i,:] / max(1, deg_r(i)) -- the mean's normalisation on its own (d_out may alias d_x).  With
+ * mpgnn_spmm(transpose=1, mean=0) it gives the backward of the mean aggregation, g_x += A_r^T (D_r^-1 g_h), for callers
+ * that compose the aggregation themselves: the all-relation RGCN baseline (model.py:132-151 `Net`, main_rgcn.py:452-472;
+ * PyG 2.3.1 RGCNConv: out = sum_r mean_r(x) W_r + x root + bias). */
+int mpgnn_scale_rows_by_degree(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t ldx, int64_t feat,
+                               float* d_out, int64_t ldout, void* stream);
+
 /* ---- K2+K3: one metapath hop, forward --------------------------------------------------
  * CustomRGCNConv.forward(layer_num, relation, x, edge_index, edge_type)
  * (mp_rgcn_layer.py:158-271) fused with the relu + dropout MPNetm applies to it

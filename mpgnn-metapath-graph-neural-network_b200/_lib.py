@@ -36,6 +36,7 @@ PROTOTYPES = {
                              _ptr, _ptr, _ptr, _i64, _ptr]),
     "mpgnn_hop_bwd": (_i32, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _u32, _dbl, _ptr,
                              _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "mpgnn_scale_rows_by_degree": (_i32, [_ptr, _i64, _ptr, _i64, _i64, _ptr, _i64, _ptr]),
     "mpgnn_hop_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "mpgnn_hop_h_rows": (_i64, [_ptr, _i64, _i64, _i64, _u32]),
     "mpgnn_graph_relation_rows": (_i32, [_ptr, _i64, _c.POINTER(_ptr), _c.POINTER(_i64)]),

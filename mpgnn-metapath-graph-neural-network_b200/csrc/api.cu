@@ -250,6 +250,16 @@ int mpgnn_spmm(const mpgnn_graph* g, int64_t relation, int transpose, int mean, 
   return launch_spmm_graph(gi, relation, transpose, mean, d_x, ldx, feat, d_init, ldinit, d_out, ldout, stream_of(stream));
 }
 
+int mpgnn_scale_rows_by_degree(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t ldx, int64_t feat,
+                               float* d_out, int64_t ldout, void* stream) {
+  MPGNN_REQUIRE(g && d_x && d_out, MPGNN_EINVAL, "scale_rows_by_degree: NULL argument");
+  const mpgnn_graph_impl* gi = impl(g);
+  MPGNN_REQUIRE(relation >= 0 && relation < gi->r, MPGNN_ERANGE, "scale_rows_by_degree: relation %lld outside [0,%lld)",
+                (long long)relation, (long long)gi->r);
+  MPGNN_REQUIRE(feat >= 1 && ldx >= feat && ldout >= feat, MPGNN_EINVAL, "scale_rows_by_degree: bad strides");
+  return launch_scale_rows_by_degree(gi, relation, d_x, ldx, feat, d_out, ldout, stream_of(stream));
+}
+
 int mpgnn_hop_fwd(const mpgnn_graph* g, int64_t relation, const float* d_x, int64_t f_in, const float* d_w,
                   const float* d_root, const float* d_bias, int64_t f_out, uint32_t flags, double dropout_p,
                   uint64_t seed, uint64_t offset, const uint8_t* d_mask_bits, float* d_h, float* d_y,

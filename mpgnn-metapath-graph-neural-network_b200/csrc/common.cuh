@@ -179,6 +179,8 @@ int launch_spmm_graph_compact(const mpgnn_graph_impl* g, int64_t rel, const floa
                               int64_t ldout, cudaStream_t s);
 int launch_spmm_graph_transpose_compact(const mpgnn_graph_impl* g, int64_t rel, const float* t_c, int64_t ldt, int64_t feat,
                                         float* out, int64_t ldout, cudaStream_t s);
+int launch_scale_rows_by_degree(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t ldx, int64_t feat, float* out,
+                                int64_t ldout, cudaStream_t s);
 static inline int64_t graph_rel_nnz_rows(const mpgnn_graph_impl* g, int64_t rel) {
   return g->rel_nz_host[rel + 1] - g->rel_nz_host[rel];
 }

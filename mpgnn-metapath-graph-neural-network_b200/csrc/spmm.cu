@@ -430,4 +430,29 @@ static int launch_spmm_skip(const int32_t* ptr, const int32_t* idx, int64_t n_ro
   return launch_vec<1>(ptr, idx, n_rows, mean, x, ldx, feat, init, ldinit, out, ldout, skip_deg, s);
 }
 
+// out[i,:] = x[i,:] / max(1, deg_r(i)): the mean's normalisation on its own, for callers that aggregate the transposed
+// way themselves (backward of the all-relation RGCN baseline: g_x += A_r^T (D_r^-1 g_h)).
+__global__ void __launch_bounds__(256) scale_rows_by_degree_kernel(const int32_t* __restrict__ ptr, int64_t n_rows,
+                                                                   const float* __restrict__ x, int64_t ldx, int64_t feat,
+                                                                   float* __restrict__ out, int64_t ldout) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * feat; i += stride) {
+    const int64_t row = i / feat, c = i - row * feat;
+    const int deg = __ldg(ptr + row + 1) - __ldg(ptr + row);
+    const float v = x[row * ldx + c];
+    out[row * ldout + c] = deg > 1 ? v / (float)deg : v;
+  }
+}
+
+int launch_scale_rows_by_degree(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t ldx, int64_t feat, float* out,
+                                int64_t ldout, cudaStream_t s) {
+  const int64_t work = g->n * feat;
+  if (work <= 0) return MPGNN_OK;
+  int64_t blocks = ceil_div(work, 256);
+  if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+  scale_rows_by_degree_kernel<<<(unsigned)blocks, 256, 0, s>>>(g->csr_ptr + rel * g->n, g->n, x, ldx, feat, out, ldout);
+  MPGNN_LAUNCH_CHECK();
+  return MPGNN_OK;
+}
+
 }  // namespace mpgnn

@@ -15,3 +15,4 @@ from .main import (Data, mpgnn_train, mpgnn_validation, mpgnn_test, mpgnn_parall
                    mpgnn_parallel_multiple_x, mpgnn_parallel_multiple_batch, device_macro_f1, CandidateTrainer)
 from .search import (score_relation_parallel, node_types_and_connected_relations, create_edge_dictionary,  # noqa: E402,F401
                      greedy_search, Comm, run_scorer)
+from . import rgcn_baseline  # noqa: E402,F401  (Net / RGCNConv: the reference's all-relation comparison model)

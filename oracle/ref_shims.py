@@ -92,6 +92,39 @@ class _MessagePassing(torch.nn.Module):
         return x_j
 
 
+class _RGCNConv(_MessagePassing):
+    """torch_geometric.nn.RGCNConv stand-in (PyG 2.3.1, third-party), for the reference's comparison model `Net`
+    (model.py:137-138): per-relation weights [R, in, out], root, bias; reset_parameters = glorot(weight), glorot(root),
+    zeros(bias); forward without decomposition and without pyg_lib (not in the reference's requirements.txt) is the
+    per-relation loop -- the very loop the reference's CustomRGCNConv was cut down from (mp_rgcn_layer.py:249-258):
+        for i in range(R): h = propagate(edge_index[:, edge_type == i], x=x); out = out + h @ weight[i]
+        out = out + x @ root + bias."""
+
+    def __init__(self, in_channels, out_channels, num_relations, num_bases=None, num_blocks=None, aggr="mean",
+                 root_weight=True, bias=True, **kwargs):
+        kwargs.setdefault("aggr", aggr)
+        super().__init__(node_dim=0, **kwargs)
+        assert num_bases is None and num_blocks is None and root_weight
+        self.in_channels, self.out_channels, self.num_relations = in_channels, out_channels, num_relations
+        self.weight = torch.nn.Parameter(torch.empty(num_relations, in_channels, out_channels))
+        self.root = torch.nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = torch.nn.Parameter(torch.empty(out_channels)) if bias else None
+        _glorot(self.weight)
+        _glorot(self.root)
+        _zeros(self.bias)
+
+    def forward(self, x, edge_index, edge_type=None):
+        out = torch.zeros(x.size(0), self.out_channels, device=x.device)
+        for i in range(self.num_relations):
+            tmp = edge_index[:, edge_type == i]
+            h = self.propagate(tmp, x=x, size=(x.size(0), x.size(0)))
+            out = out + (h @ self.weight[i])
+        out = out + x @ self.root
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
 def _glorot(t):
     if isinstance(t, torch.Tensor):
         a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
@@ -145,7 +178,7 @@ def install():
 
     tg = _mod("torch_geometric")
     tg.data = _mod("torch_geometric.data", Data=_Data)
-    tg.nn = _mod("torch_geometric.nn", RGCNConv=_Dummy)
+    tg.nn = _mod("torch_geometric.nn", RGCNConv=_RGCNConv)
     tg.nn.conv = _mod("torch_geometric.nn.conv", MessagePassing=_MessagePassing)
     tg.nn.inits = _mod("torch_geometric.nn.inits", glorot=_glorot, zeros=_zeros)
     tg.typing = _mod("torch_geometric.typing", Adj=object, OptTensor=object)
