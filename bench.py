@@ -620,9 +620,9 @@ def run_reference(args):
         return
     n, e, r, f = WORKLOADS["c4"]
     # full C4 needs ~90 GB of host memory at its peak (x, g_y, the int64 edge list, and every intermediate the
-    # reference materialises and autograd keeps); below 200 GB available the sample is the same shape at 1/10 scale
+    # reference materialises and autograd keeps); below 150 GB available the sample is the same shape at 1/10 scale
     mem = _host_memory_gb()
-    workload = "c4" if mem >= 200.0 and not args.tenth else "c4_tenth"
+    workload = "c4" if mem >= 150.0 and not args.tenth else "c4_tenth"
     cpu = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1), budget_s=150.0, workload=workload)
     cpu["host_memory_gb"] = mem
     line = {
