@@ -332,10 +332,12 @@ def _bag_sources(bags):
     return mask
 
 
-def _bag_restart_loop(data, relation, features_dim, seed, max_restarts=None, device=None, record=None):
+def _bag_restart_loop(data, relation, features_dim, seed, max_restarts=None, device=None, record=None, restart_fn=None):
     """Shared body of score_relation_bags_parallel (restarts until two non-improvements, freezing)
     and retrain_bags (exactly one restart, no freezing)."""
-    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if restart_fn is None:
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    restart_fn = restart_fn or run_bag_restart
     random.seed(seed)
     torch.manual_seed(seed)
     source_nodes_mask = _bag_sources(data.bags)
@@ -347,14 +349,14 @@ def _bag_restart_loop(data, relation, features_dim, seed, max_restarts=None, dev
     grad_mask = torch.ones(n, dtype=torch.uint8)
     labels_list = bag_labels.reshape(-1).tolist()
     v = len(bags) == 1 or (len(bags) > 1 and labels_list.count(1) == 0)
-    graph = _graph_of(data, device)
-    x_dev = data.x.to(device=device, dtype=torch.float32).contiguous()
+    graph = _graph_of(data, device) if restart_fn is run_bag_restart else None
+    x_dev = data.x.to(device=device, dtype=torch.float32).contiguous() if restart_fn is run_bag_restart else data.x
     predictions_for_each_restart, frozen = {}, []
     rest, current_loss, restarts, lin = 0, 100.0, 0, None
     trained_w = weights
     while rest < 2 and len(bags) > 0:
         lin0 = torch.nn.Linear(int(features_dim), 1, bias=False).weight.detach()[0].clone()   # Score.__init__
-        traj, trained_w, lin, best_dst, loss_per_bag, src_val = run_bag_restart(
+        traj, trained_w, lin, best_dst, loss_per_bag, src_val = restart_fn(
             graph, relation, bags, bag_labels, x_dev, weights, lin0, grad_mask, bool(frozen))
         loss = float(traj[-1])
         if record is not None:
@@ -396,19 +398,22 @@ def _bag_restart_loop(data, relation, features_dim, seed, max_restarts=None, dev
     return current_loss, model, predictions_for_each_restart, v
 
 
-def score_relation_bags_parallel(data_object, relation, features_dim, dataset, metapath_len=1, device=None, record=None):
+def score_relation_bags_parallel(data_object, relation, features_dim, dataset, metapath_len=1, device=None, record=None,
+                                 restart_fn=None):
     """main.py:853-917 -> (relation, best loss, model, predictions_for_each_restart, skip flag)."""
     loss, model, preds, v = _bag_restart_loop(data_object, int(relation), features_dim,
-                                              bag_seed(metapath_len, relation), device=device, record=record)
+                                              bag_seed(metapath_len, relation), device=device, record=record,
+                                              restart_fn=restart_fn)
     return int(relation), loss, model, preds, v
 
 
-def retrain_bags(data, relation, best_pred_for_each_restart, BAGS, features_dim, dataset, metapath_len=1, device=None):
+def retrain_bags(data, relation, best_pred_for_each_restart, BAGS, features_dim, dataset, metapath_len=1, device=None,
+                 restart_fn=None):
     """main.py:814-850: one more restart of 50 epochs; its per-source values are appended to the
     predictions collected while scoring."""
     _, _, preds, _ = _bag_restart_loop(data, int(relation), features_dim,
                                        bag_seed(metapath_len, relation) + RETRAIN_SEED_SHIFT, max_restarts=1,
-                                       device=device)
+                                       device=device, restart_fn=restart_fn)
     for key, vals in preds.items():
         best_pred_for_each_restart.setdefault(key, []).extend(vals)
     return best_pred_for_each_restart
@@ -556,32 +561,145 @@ def make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_out
     return union_fn
 
 
+class _HostPipeline:
+    """The search stage on the reference-named dictionary functions above (host Python around the K5 kernels); also
+    what the tests drive with injected stand-in scorers."""
+
+    def __init__(self, data, input_dim, dataset, score_fn, bag_score_fn):
+        self.data, self.input_dim, self.dataset = data, input_dim, dataset
+        self.dict_fn = None
+        if score_fn is None:
+            def score_fn(d, rel):            # the loss only: no dictionaries for relations the gap rule will drop
+                return score_relation_parallel(d, rel, d.source_nodes_mask, input_dim, dataset, dictionaries=False)[1]
+
+            def dict_fn(d, rel):             # what score_relation_parallel returns next to the loss (main.py:733-737)
+                sources = list(d.source_nodes_mask) or np.unique(_np(d.edge_index)[0][_np(d.edge_type) == int(rel)]).tolist()
+                return create_edge_dictionary(d, rel, sources, BAGS=False, dataset=dataset)
+            self.dict_fn = dict_fn
+        if bag_score_fn is None:
+            def bag_score_fn(bag_data, rel, mlen):
+                return score_relation_bags_parallel(bag_data, rel, input_dim, dataset, metapath_len=mlen)
+        self.score_fn, self.bag_score_fn = score_fn, bag_score_fn
+        self.local_out = {}
+
+    def actual_relations(self):
+        return node_types_and_connected_relations(self.data, BAGS=False, dataset=self.dataset)
+
+    def score_step0(self, rel):
+        out = self.score_fn(self.data, rel)
+        self.local_out[rel] = out
+        return out[0] if isinstance(out, tuple) else out
+
+    def init_state(self, rel):
+        out = self.local_out.get(rel)
+        if not isinstance(out, tuple) and self.dict_fn is not None:
+            out = (out,) + tuple(self.dict_fn(self.data, rel))       # dictionaries of the kept relations only
+        elif not isinstance(out, tuple):                             # scored on another rank: recompute locally
+            out = self.score_fn(self.data, rel)                      # (deterministic under the per-relation seed)
+        if not isinstance(out, tuple):
+            return None                                              # stand-in scorer without dictionaries: no bag steps
+        return [out[1], out[2], _copy_bag(self.data)]
+
+    def make_bags(self, st):
+        create_bags(st[0], st[1], st[2])                                                      # main.py:1385
+        return node_types_and_connected_relations(st[2], BAGS=True, dataset=self.dataset)     # main.py:1386
+
+    def score_bag(self, st, rel, mlen):
+        res = self.bag_score_fn(st[2], rel, mlen)
+        return float(res[1]), bool(res[4]), res
+
+    def accept(self, st, rel, mlen, res):
+        if res is None:
+            res = self.bag_score_fn(st[2], rel, mlen)                                          # other rank's relation
+        data_copy = _copy_bag(st[2])
+        preds = {kk: list(vv) for kk, vv in res[3].items()}
+        preds = retrain_bags(data_copy, rel, preds, True, self.input_dim, self.dataset, metapath_len=mlen)
+        src_mask, _ = relabel_nodes_inside_bags(preds, data_copy, res[2])
+        e2, d2 = create_edge_dictionary(data_copy, rel, src_mask, BAGS=False, dataset=self.dataset)   # main.py:1433
+        e2, d2 = clean_dictionaries(data_copy, e2, d2, res[2])
+        return [e2, d2, data_copy]
+
+
+class _DevicePipeline:
+    """The same stage with its state kept as arrays on the device (search_device.py): no dictionaries, bulk draws from
+    Python's own generator, K5 fed from device tensors.  Decisions and losses are those of the host pipeline (CPU test:
+    tests/test_search_device_cpu.py; GPU test: test_gpu_search_bags.py)."""
+
+    def __init__(self, data, input_dim, dataset, device):
+        from . import search_device as sd
+        self.sd = sd
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.data, self.input_dim, self.dataset = data, input_dim, dataset
+        self.graph = _graph_of(data, self.device)
+        ei = data.edge_index if not isinstance(data.edge_index, RelationGraph) else None
+        if ei is None:
+            raise ValueError("the device search pipeline needs the raw edge_index / edge_type tensors on the data bag")
+        self.sg = sd.SearchGraph(ei, data.edge_type, int(data.num_nodes), self.device)
+        self.labels = torch.as_tensor(_np(data.labels).reshape(-1)).to(self.device, torch.float32)
+        self.sources = [int(v) for v in data.source_nodes_mask]
+        self.x_dev = data.x.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def actual_relations(self):
+        if self.dataset == "synthetic":
+            keep = self.labels[self.sg.rows_all] == 1                                          # main.py:72
+        else:
+            member = torch.zeros(self.sg.n, dtype=torch.bool, device=self.device)
+            member[torch.as_tensor(self.sources, dtype=torch.int64, device=self.device)] = True
+            keep = member[self.sg.rows_all]                                                    # main.py:80
+        return self.sg.connected_relations_from_edge_mask(keep)
+
+    def score_step0(self, rel):
+        random.seed(SCORER_SEED_BASE + int(rel))
+        w, mask, node_labels = self.sd.step0_inputs(self.sg, int(rel), self.labels, self.sources, self.dataset)
+        traj, _, _ = run_scorer(self.graph, int(rel), w, node_labels, mask)
+        return float(traj[-1])
+
+    def init_state(self, rel):
+        return self.sd.step0_state(self.sg, int(rel), self.labels, self.sources, self.dataset)
+
+    def make_bags(self, st):
+        self.sd.create_bags(self.sg, st)
+        return self.sg.connected_relations(self.sd.bag_member_mask(self.sg, st))
+
+    def score_bag(self, st, rel, mlen):
+        loss, lin, vals, visited, skip = self.sd.bag_restart_loop(self.sg, self.graph, st, int(rel), self.x_dev,
+                                                                  self.input_dim, bag_seed(mlen, rel))
+        return float(loss), bool(skip), (lin, vals, visited)
+
+    def accept(self, st, rel, mlen, res):
+        if res is None:
+            res = self.score_bag(st, rel, mlen)[2]
+        lin, vals, visited = res
+        _, _, vals_r, _, _ = self.sd.bag_restart_loop(self.sg, self.graph, st.copy(), int(rel), self.x_dev, self.input_dim,
+                                                      bag_seed(mlen, rel) + RETRAIN_SEED_SHIFT, max_restarts=1)
+        return self.sd.accept_relation(self.sg, st, int(rel), lin, torch.cat([vals, vals_r]), visited, self.x_dev,
+                                       self.dataset)
+
+
 def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, dataset, comm=None,
                   score_fn=None, eval_fn=None, union_fn=None, bag_score_fn=None, log=None, max_depth=3,
-                  final_dict=None, select=True, epochs=None):
+                  final_dict=None, select=True, epochs=None, pipeline="device", device=None, timings=None):
     """main.py:1289-1476.  `final_dict` (main.py:1208): the {str(metapath): validation F1} table; the reference creates
     it ONCE before its loop over the one-vs-rest label sets and every label set's candidates are merged into it, so
     the driver passes the same dict to every call with `select=False` and runs `final_selection` once after the
     loop (main.py:1463-1476); with the defaults (one label set) the call does both.
+    `pipeline`: "device" keeps the search state as arrays on the GPU (search_device.py), "host" uses the dictionary
+    functions of this module; injected scorers always take the host pipeline.
     `score_fn(data, rel)` -> (loss, edge_dict, dest_dict) or a bare loss,
     `bag_score_fn(bag_data, rel, metapath_len)` -> (rel, loss, model, predictions, skip),
     `eval_fn(meta)` -> validation macro-F1, `union_fn(metas)` -> test macro-F1 default to the device
     implementations; tests inject CPU stand-ins to exercise the fan-out and the rules.
-    `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381)."""
+    `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381).  `timings` (dict, optional) receives
+    the seconds spent in the search stage and in the candidate evaluation."""
+    import time
     from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_batch, EPOCHS_PER_CANDIDATE
     epochs = epochs or EPOCHS_PER_CANDIDATE          # main.py:1121
     comm = comm or Comm()
-    dict_fn = None
-    if score_fn is None:
-        def score_fn(d, rel):            # the loss only: no dictionaries for relations the gap rule will drop
-            return score_relation_parallel(d, rel, d.source_nodes_mask, input_dim, dataset, dictionaries=False)[1]
-
-        def dict_fn(d, rel):             # what score_relation_parallel returns next to the loss (main.py:733-737)
-            sources = list(d.source_nodes_mask) or np.unique(_np(d.edge_index)[0][_np(d.edge_type) == int(rel)]).tolist()
-            return create_edge_dictionary(d, rel, sources, BAGS=False, dataset=dataset)
-    if bag_score_fn is None:
-        def bag_score_fn(bag_data, rel, mlen):
-            return score_relation_bags_parallel(bag_data, rel, input_dim, dataset, metapath_len=mlen)
+    t_start = time.time()
+    if score_fn is None and bag_score_fn is None and pipeline == "device":
+        pipe = _DevicePipeline(data, input_dim, dataset, device)
+    else:
+        pipe = _HostPipeline(data, input_dim, dataset, score_fn, bag_score_fn)
     batch_eval = None
     if eval_fn is None:
         def eval_fn(meta):
@@ -595,15 +713,11 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     if union_fn is None:
         union_fn = make_union_fn(data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, epochs=epochs)
     # ---- step 0: every rank scores its share of the relations (main.py:1319-1328) ----------
-    actual_relations = node_types_and_connected_relations(data, BAGS=False, dataset=dataset)
+    actual_relations = pipe.actual_relations()
     local = relation_split(actual_relations, comm.size, comm.rank)
-    local_out = {}
     mine = []
     for rel in local:
-        out = score_fn(data, rel)
-        loss = out[0] if isinstance(out, tuple) else out
-        local_out[rel] = out
-        mine.append([float(rel), float(loss)])
+        mine.append([float(rel), float(pipe.score_step0(rel))])
     gathered = comm.allgather_records(mine, 2, max(1, len(actual_relations)))
     final_result = [(int(r), l) for part in gathered for r, l in part]      # sum(result, []) in rank order
     best = gap_select_step0([r for r, _ in final_result], [l for _, l in final_result])
@@ -618,20 +732,15 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
         # per-metapath state the reference keeps in current_metapaths_dict: edge dict, dest dict, data copy
         state = {}
         for rel in best:
-            out = local_out.get(rel)
-            if not isinstance(out, tuple) and dict_fn is not None:
-                out = (out,) + tuple(dict_fn(data, rel))         # dictionaries of the kept relations only
-            elif not isinstance(out, tuple):                     # scored on another rank: recompute locally
-                out = score_fn(data, rel)                        # (deterministic under the per-relation seed)
-            if not isinstance(out, tuple):
-                state = None                                     # stand-in scorer without dictionaries: no bag steps
+            st = pipe.init_state(rel)
+            if st is None:
+                state = None
                 break
-            state[str([rel])] = [out[1], out[2], _copy_bag(data)]
+            state[str([rel])] = st
         for k in range(max_depth if state is not None else 0):
             for meta in list(current_metapaths_list):
-                edg, dst, bag_data = state[str(meta)]
-                create_bags(edg, dst, bag_data)                                           # main.py:1385
-                rels_k = node_types_and_connected_relations(bag_data, BAGS=True, dataset=dataset)
+                st = state[str(meta)]
+                rels_k = pipe.make_bags(st)
                 final_metapaths_list.append(list(meta))                                   # main.py:1388 (duplicates)
                 intermediate.remove(meta)
                 if not rels_k:
@@ -639,10 +748,10 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
                 local_k = relation_split(rels_k, comm.size, comm.rank)
                 cache, mine = {}, []
                 for rel in local_k:
-                    res = bag_score_fn(bag_data, rel, len(meta))
+                    loss, skip, res = pipe.score_bag(st, rel, len(meta))
                     cache[rel] = res
-                    if not res[4]:                                                        # skip flag (main.py:1405)
-                        mine.append([float(rel), float(res[1])])
+                    if not skip:                                                          # skip flag (main.py:1405)
+                        mine.append([float(rel), float(loss)])
                 gathered = comm.allgather_records(mine, 2, max(1, len(rels_k)))
                 result_k = [(int(r), l) for part in gathered for r, l in part]
                 accepted = accept_bag_relations(result_k)
@@ -658,15 +767,11 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
                     intermediate.append(tmp_meta)
                     if tmp_meta not in final_metapaths_list:
                         final_metapaths_list.append(tmp_meta)
-                    res = cache.get(rel) or bag_score_fn(bag_data, rel, len(meta))        # other rank's relation
-                    data_copy = _copy_bag(bag_data)
-                    preds = {kk: list(vv) for kk, vv in res[3].items()}
-                    preds = retrain_bags(data_copy, rel, preds, True, input_dim, dataset, metapath_len=len(meta))
-                    src_mask, _ = relabel_nodes_inside_bags(preds, data_copy, res[2])
-                    e2, d2 = create_edge_dictionary(data_copy, rel, src_mask, BAGS=False, dataset=dataset)  # main.py:1433
-                    e2, d2 = clean_dictionaries(data_copy, e2, d2, res[2])
-                    state[str(tmp_meta)] = [e2, d2, data_copy]
+                    state[str(tmp_meta)] = pipe.accept(st, rel, len(meta), cache.get(rel))
             current_metapaths_list = [list(m) for m in intermediate]
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t_search = time.time()
     # ---- evaluation: contiguous candidate blocks (main.py:1444-1462) -------------------------
     lo, hi = candidate_block(len(final_metapaths_list), comm.size, comm.rank)
     done = {}
@@ -691,8 +796,15 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     if log:
         log("candidates: %s" % {k: round(v, 6) for k, v in final_dict.items()})
     # ---- final selection (rank 0 in the reference; replicated here, it is deterministic) ----
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t_eval = time.time()
     f_meta, test_f1 = final_selection(final_dict, union_fn) if select else (None, None)
     if log and select:
         log("final meta: %s test acc: %s" % (f_meta, test_f1))
+    if timings is not None:
+        timings.update(search_s=t_search - t_start, evaluation_s=t_eval - t_search, selection_s=time.time() - t_eval,
+                       relations_scored=len(step0["relations"]) + sum(len(st_["relations"]) for st_ in steps),
+                       candidates=len(final_metapaths_list))
     return {"relations": step0["relations"], "losses": step0["losses"], "kept": best, "bag_steps": steps,
             "candidates": final_metapaths_list, "final_dict": final_dict, "final_meta": f_meta, "test_f1": test_f1}

@@ -80,3 +80,73 @@ def test_greedy_search_recovers_ground_truth_metapath(fx3):
     assert [1, 0] in res["candidates"]                       # the generator's ground truth (metapath.dat: "1 0")
     assert res["final_dict"]["[1, 0]"] > 0.99
     assert res["final_meta"][0] == [1, 0] and res["test_f1"] > 0.99
+
+
+@pytest.mark.parametrize("rel0", [0, 1])
+def test_device_pipeline_bag_scorer_matches_reference_golden(fx3, rel0):
+    """The array form of the search state (search_device.py) feeding K5 from device tensors, against the same reference
+    golden as the dictionary form above: bags, candidate relations, and for every relation every restart's loss
+    trajectory, freeze set and trained weights."""
+    from mpgnn_b200 import search_device as sd
+    g = load_golden("search_bags_len3")
+    data = _data(fx3)
+    dev = torch.device("cuda")
+    sg = sd.SearchGraph(fx3["edge_index"], fx3["edge_type"], fx3["x"].size(0), dev)
+    graph = search._graph_of(data, dev)
+    x_dev = fx3["x"].to(dev)
+    lab = fx3["labels"].float().to(dev)
+    state = sd.step0_state(sg, rel0, lab, [], "synthetic")
+    sd.create_bags(sg, state)
+    pre = "m%d_" % rel0
+    assert state.bags_as_lists() == _unragged(g[pre + "bags_flat"], g[pre + "bags_ptr"])
+    assert state.bag_labels.tolist() == g[pre + "bag_labels"].tolist()
+    rels = sg.connected_relations(sd.bag_member_mask(sg, state))
+    assert rels == g[pre + "relations"].tolist()
+    for rr in rels:
+        tag = pre + "r%d_" % rr
+        rec = {}
+        loss, lin, vals, visited, skip = sd.bag_restart_loop(sg, graph, state, rr, x_dev, 2, search.bag_seed(1, rr), record=rec)
+        assert rec["dest_keys"].tolist() == g[tag + "dest_keys"].tolist()
+        ref = g[tag + "loss_traj"]
+        got = np.array(rec["traj"])
+        n_restarts = int(g[tag + "n_restarts"])
+        assert len(got) == len(ref) == 50 * n_restarts
+        assert np.allclose(got, ref, rtol=1e-4, atol=1e-7), float(np.abs(got - ref).max())
+        fz_ptr, fz_flat = g[tag + "frozen_ptr"], g[tag + "frozen_flat"]
+        keys = g[tag + "dest_keys"]
+        for k in range(n_restarts):
+            assert sorted(torch.nonzero(rec["frozen"][k]).reshape(-1).tolist()) == sorted(fz_flat[fz_ptr[k]:fz_ptr[k + 1]].tolist())
+            assert np.allclose(rec["w"][k].cpu().numpy()[keys], g[tag + "w_hist"][k], atol=2e-6), (tag, k)
+        assert abs(loss - float(g[tag + "loss"])) <= 1e-4 * float(g[tag + "loss"]) + 1e-8
+        assert bool(skip) == bool(g[tag + "skip"])
+        assert visited.tolist() == g[tag + "pred_keys"].tolist()
+        pp, pv = g[tag + "pred_ptr"], g[tag + "pred_vals"]
+        vals_h = vals.cpu().numpy()
+        for i, key in enumerate(visited.tolist()):
+            assert np.allclose(vals_h[:, key], pv[pp[i]:pp[i + 1]], atol=1e-5), (tag, key)
+
+
+@pytest.mark.parametrize("case", ["fixture", "fb"])
+def test_device_pipeline_decides_exactly_like_host_pipeline(fx3, case):
+    """greedy_search through both pipelines (two bag iterations, candidate evaluation stubbed out): same relations,
+    bit-identical losses, same accepted relations and candidate list."""
+    if case == "fixture":
+        data, f, ds, nrel = _data(fx3), 2, "synthetic", 4
+    else:
+        g = load_golden("search_fb_small")
+        x = torch.from_numpy(g["x"])
+        data = mpgnn_b200.Data(x=x, edge_index=torch.from_numpy(g["edge_index"]), edge_type=torch.from_numpy(g["edge_type"]),
+                               labels=torch.from_numpy(g["labels"]).unsqueeze(-1), num_nodes=x.size(0),
+                               source_nodes_mask=g["labelled"].tolist())
+        f, ds, nrel = x.size(1), "fb15k-237", 12
+    out = {}
+    for pipe in ("host", "device"):
+        tm = {}
+        out[pipe] = search.greedy_search(data, None, f, 64, nrel, 64, 2, ds, eval_fn=lambda meta: 0.5 + 0.001 * sum(meta),
+                                         union_fn=lambda metas: 0.9, max_depth=2 if case == "fixture" else 1, pipeline=pipe,
+                                         timings=tm)
+        print(case, pipe, "search %.2f s for %d relation scorings" % (tm["search_s"], tm["relations_scored"]))
+    h, d = out["host"], out["device"]
+    assert h["relations"] == d["relations"] and h["kept"] == d["kept"] and h["losses"] == d["losses"]
+    assert h["bag_steps"] == d["bag_steps"]
+    assert h["candidates"] == d["candidates"] and h["final_meta"] == d["final_meta"]
