@@ -329,6 +329,10 @@ def run_ours(args):
 
     cand = None if args.no_candidates else candidate_scoring(rank, world, dev, dist)
     rels = None if args.no_candidates else relation_scoring(rank, world, dev, dist)
+    c5 = None
+    if args.search:
+        torch.cuda.empty_cache()
+        c5 = search_c5(rank, world, dev, dist)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -410,7 +414,7 @@ def run_ours(args):
                   "mean_rows_with_edges": nnz_mean,
                   "graph_build_s": build_s, "rows_per_s": n * args.steps * world / (ms * 1e-3),
                   "mean_edges_per_hop": e_r_mean, "kernels": per_kernel, "spmm_mean_fwd_roofline": spmm_roof,
-                  "candidate_scoring": cand, "relation_scoring": rels},
+                  "candidate_scoring": cand, "relation_scoring": rels, "search_c5": c5},
     }
     emit(line)
 
@@ -546,6 +550,53 @@ def _host_memory_gb():
     return avail or 0.0
 
 
+def search_c5(rank, world, dev, dist, depth=3, epochs=999):
+    """BASELINE.json configs[4]: the FULL greedy metapath search (main.py:1289-1476) on a synthetic graph of 1M nodes x
+    100 relations, metapaths up to length 4 (three bag iterations), relations and candidates sharded over the ranks with
+    one small all-gather of (id, score) records per step (NCCL).  Graph: the reference generator's rules
+    (mpgnn_b200.synthetic) with 100 relations (25 disjoint ones per colour pair), out-degree uniform in 1..19 (E ~ 10 N
+    before sparsification), a planted length-3 metapath and its labels; 10 % test / 18 % validation / 72 % train.
+    Strong scaling: the work is fixed, the ranks split it."""
+    import mpgnn_b200
+    from mpgnn_b200 import synthetic, search
+    t0 = time.time()
+    sg = synthetic.generate(1_000_000, 19, "red-blue-red-blue", 0, 0, seed=5, presets=synthetic.disjoint_presets(100))
+    x, ei, et, y = sg.tensors()
+    n, e = sg.num_nodes, int(ei.size(1))
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5))
+    n_te, n_va = n // 10, (n - n // 10) // 5
+    data_mpgnn = mpgnn_b200.Data(x=x, edge_index=ei, edge_type=et, num_nodes=n,
+                                 test_idx=perm[:n_te], test_y=y[perm[:n_te]], val_idx=perm[n_te:n_te + n_va],
+                                 val_y=y[perm[n_te:n_te + n_va]], train_idx=perm[n_te + n_va:], train_y=y[perm[n_te + n_va:]])
+    data = mpgnn_b200.Data(x=x, edge_index=ei, edge_type=et, labels=y.unsqueeze(-1), num_nodes=n, source_nodes_mask=[])
+    gen_s = time.time() - t0
+    comm = search.Comm(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tm, logs = {}, []
+    t1 = time.time()
+    res = search.greedy_search(data, data_mpgnn, 2, 64, 100, 64, 2, "synthetic", comm=comm, max_depth=depth, epochs=epochs,
+                               timings=tm, log=logs.append if rank == 0 else None)
+    torch.cuda.synchronize()
+    dt = time.time() - t1
+    parts = [dt, tm["search_s"], tm["evaluation_s"], tm["selection_s"]]
+    if world > 1:
+        t = torch.tensor(parts, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parts = t.tolist()
+    return {"seconds": parts[0], "search_stage_s": parts[1], "evaluation_stage_s": parts[2], "final_selection_s": parts[3],
+            "relations_scored": tm["relations_scored"], "relations_per_s": tm["relations_scored"] / max(parts[1], 1e-9),
+            "candidates_trained": len({str(c) for c in res["candidates"]}), "candidate_list_length": len(res["candidates"]),
+            "candidates_per_s": len({str(c) for c in res["candidates"]}) / max(parts[2], 1e-9),
+            "epochs_per_candidate": epochs, "kept_step0": res["kept"], "bag_steps": len(res["bag_steps"]),
+            "final_meta": res["final_meta"], "test_f1": res["test_f1"], "planted": sg.planted_relations,
+            "final_dict": {k: round(v, 6) for k, v in res["final_dict"].items()}, "scaling": "strong",
+            "graph": "%d nodes / %d edges / 100 relations (generator rules, seed 5), %d positives; generated in %.1f s"
+                     % (n, e, int(y.sum()), gen_s),
+            "log": logs}
+
+
 def cpu_baseline(steps, warmup, budget_s, workload="c4_tenth"):
     """The reference's CPU path for the same step on the host cores: CustomRGCNConv.forward (mp_rgcn_layer.py:158-271:
     O(E) relation filter, PyG scatter-mean, two mm) + relu + Dropout(0.6) as MPNetm applies them (model.py:210-214) and
@@ -671,6 +722,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tenth", action="store_true", help="reference arm: force the 1/10-scale sample")
     ap.add_argument("--no-candidates", action="store_true", help="skip the candidate-scoring (C2 shape) measurement")
+    ap.add_argument("--search", action="store_true",
+                    help="also run BASELINE configs[4]: the full greedy search on 1M nodes x 100 relations (minutes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -523,6 +523,25 @@ def candidate_block(n_items, size, rank):
     return start, start + sub + (1 if rank < rem else 0)
 
 
+def lpt_assignment(metapaths, size):
+    """Longest-processing-time-first spread of the DISTINCT candidates over `size` ranks (a candidate costs one hop
+    forward + backward per relation per epoch, i.e. its length): every rank gets the list positions it reports, all
+    positions of a repeated metapath going to the rank that trains it.  Deterministic (ties: first position first,
+    lowest rank first)."""
+    first, positions = {}, {}
+    for i, m in enumerate(metapaths):
+        key = tuple(int(v) for v in m)
+        first.setdefault(key, i)
+        positions.setdefault(key, []).append(i)
+    order = sorted(first, key=lambda k: (-len(k), first[k]))
+    load, out = [0] * size, [[] for _ in range(size)]
+    for key in order:
+        r = min(range(size), key=lambda q: (load[q], q))
+        load[r] += len(key)
+        out[r].extend(positions[key])
+    return [sorted(v) for v in out]
+
+
 def gap_select_step0(relations, losses):
     """main.py:1346-1355 (`<=` at step 0; keep everything with fewer than two gaps)."""
     accs = sorted(losses)
@@ -678,7 +697,8 @@ class _DevicePipeline:
 
 def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, dataset, comm=None,
                   score_fn=None, eval_fn=None, union_fn=None, bag_score_fn=None, log=None, max_depth=3,
-                  final_dict=None, select=True, epochs=None, pipeline="device", device=None, timings=None):
+                  final_dict=None, select=True, epochs=None, pipeline="device", device=None, timings=None,
+                  assignment=None):
     """main.py:1289-1476.  `final_dict` (main.py:1208): the {str(metapath): validation F1} table; the reference creates
     it ONCE before its loop over the one-vs-rest label sets and every label set's candidates are merged into it, so
     the driver passes the same dict to every call with `select=False` and runs `final_selection` once after the
@@ -690,7 +710,11 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     `eval_fn(meta)` -> validation macro-F1, `union_fn(metas)` -> test macro-F1 default to the device
     implementations; tests inject CPU stand-ins to exercise the fan-out and the rules.
     `max_depth` = number of bag iterations (`for k in range(3)`, main.py:1381).  `timings` (dict, optional) receives
-    the seconds spent in the search stage and in the candidate evaluation."""
+    the seconds spent in the search stage and in the candidate evaluation.
+    `assignment`: how the candidates are spread over the ranks -- "block" = the reference's contiguous blocks
+    (main.py:1444-1450: the long metapaths are appended last and land on the last ranks), "lpt" = distinct candidates,
+    longest first, each to the least loaded rank.  A candidate's score does not depend on who trains it (per-candidate
+    seed), so both give the same table; default "lpt" with the built-in trainer, "block" with an injected eval_fn."""
     import time
     from .main import mpgnn_parallel_multiple, mpgnn_parallel_multiple_batch, EPOCHS_PER_CANDIDATE
     epochs = epochs or EPOCHS_PER_CANDIDATE          # main.py:1121
@@ -773,17 +797,22 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
         torch.cuda.synchronize()
     t_search = time.time()
     # ---- evaluation: contiguous candidate blocks (main.py:1444-1462) -------------------------
-    lo, hi = candidate_block(len(final_metapaths_list), comm.size, comm.rank)
+    assignment = assignment or ("lpt" if batch_eval is not None else "block")
+    if assignment == "lpt":
+        my_items = lpt_assignment(final_metapaths_list, comm.size)[comm.rank]
+    else:
+        lo, hi = candidate_block(len(final_metapaths_list), comm.size, comm.rank)
+        my_items = list(range(lo, hi))
     done = {}
     mine = []
     if batch_eval is not None:
         uniq = []
-        for i in range(lo, hi):
+        for i in my_items:
             if final_metapaths_list[i] not in uniq:
                 uniq.append(final_metapaths_list[i])
         for meta, f1 in zip(uniq, batch_eval(uniq)):
             done[str(meta)] = float(f1)
-    for i in range(lo, hi):
+    for i in my_items:
         key = str(final_metapaths_list[i])
         if key not in done:                       # duplicates (main.py:1388) train to the same number under the seam
             done[key] = float(eval_fn(final_metapaths_list[i]))

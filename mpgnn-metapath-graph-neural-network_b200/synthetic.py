@@ -216,9 +216,19 @@ def _write_tsv(path, table, trailing_tab=False):
                     write_options=pacsv.WriteOptions(include_header=False, delimiter="\t", quoting_style="none"))
 
 
-def generate(num_nodes, max_rel_for_node, metapath, overlap, shared_relations, seed=0, sparsification=True):
-    """The reference script's `main(args)` with a seed: draw the graph, plant the metapath, label, sparsify."""
-    presets = relation_presets(overlap, shared_relations)
+def disjoint_presets(num_relations):
+    """num_relations / 4 relations per colour pair, no relation shared between pairs: the reference's (overlap 0,
+    shared 0) preset `([0], [1], [2], [3])` scaled up (configs with more relations than the 16 presets hold)."""
+    if num_relations < 4 or num_relations % 4 != 0:
+        raise ValueError("num_relations must be a positive multiple of 4")
+    q = num_relations // 4
+    return tuple(list(range(i * q, (i + 1) * q)) for i in range(4))
+
+
+def generate(num_nodes, max_rel_for_node, metapath, overlap, shared_relations, seed=0, sparsification=True, presets=None):
+    """The reference script's `main(args)` with a seed: draw the graph, plant the metapath, label, sparsify.
+    `presets` (four relation-id lists, one per colour pair) replaces the (overlap, shared_relations) table entry."""
+    presets = relation_presets(overlap, shared_relations) if presets is None else presets
     rng = np.random.Generator(np.random.PCG64(int(seed)))
     meta_rev, cols_rev = plant_metapath(metapath, presets, rng)        # drawn first, as in the reference (:196)
     colors, triplets = draw_graph(num_nodes, max_rel_for_node, presets, rng)

@@ -370,3 +370,17 @@ def test_greedy_search_builds_dictionaries_for_kept_relations_only(fx3, monkeypa
     for key in ("relations", "losses", "kept", "candidates", "final_dict", "final_meta"):
         assert res_fast[key] == res_full[key], key
     assert bags_fast == bags_full and len(bags_fast) > 0
+
+
+def test_lpt_assignment_covers_every_position_once_and_balances():
+    metas = [[0], [1], [0], [2, 0], [3, 0], [1, 2, 0], [4, 2, 0], [2, 0], [5, 1, 2, 0]]
+    for size in (1, 2, 3, 8):
+        parts = search.lpt_assignment(metas, size)
+        assert sorted(i for p in parts for i in p) == list(range(len(metas)))
+        for p in parts:                                     # all copies of a metapath on one rank
+            for i in p:
+                assert all(j in p for j, m in enumerate(metas) if m == metas[i])
+    two = search.lpt_assignment(metas, 2)
+    load = [sum(len(m) for m in {tuple(metas[i]) for i in p}) for p in two]
+    assert abs(load[0] - load[1]) <= 1
+    assert search.lpt_assignment(metas, 2) == two           # deterministic
