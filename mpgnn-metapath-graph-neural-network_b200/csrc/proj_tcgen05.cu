@@ -606,7 +606,11 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   // halves do: the pair converts each A tile once for all 128 columns.  Opt-in (MPGNN_PROJ_PAIR=1): correct and
   // tested, but at C4 it runs at the single-CTA kernel's 3.6 ms -- with the conversions halved the stage loop
   // (converter -> remote arrive -> MMA -> multicast commit -> converter) is what bounds it, see DESIGN.md 4.2.
+#ifdef MPGNN_TC_EXPERIMENT      // profiling builds only (scripts/exp_variants.sh): the product library carries no pair kernels
   static const bool pair_ok = getenv("MPGNN_PROJ_PAIR") != nullptr && atoi(getenv("MPGNN_PROJ_PAIR")) != 0;
+#else
+  const bool pair_ok = false;
+#endif
   const bool pair = pair_ok && bn == 64 && a.n % 128 == 0 && k * 64 * 8 <= tc::kMaxBBytes && a.a1_actmask == nullptr &&
                     a.deg_ptr == nullptr;
   const int bnb = pair ? 64 : bn;              // B columns resident per CTA
@@ -694,6 +698,7 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
     MPGNN_REQUIRE(p.dropout_mode == 0, MPGNN_ENOTSUP, "proj_tcgen05: operand mask with a dropout epilogue");
     return deg ? launch(tc::gemm_rows_tc_kernel<0, true, true>) : launch(tc::gemm_rows_tc_kernel<0, false, true>);
   }
+#ifdef MPGNN_TC_EXPERIMENT
   if (pair) {
     switch (p.dropout_mode) {
       case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false, true>);
@@ -701,6 +706,7 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
       default: return launch(tc::gemm_rows_tc_kernel<2, false, false, true>);
     }
   }
+#endif
   switch (p.dropout_mode * 2 + (deg ? 1 : 0)) {
     case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false>);
     case 1: return launch(tc::gemm_rows_tc_kernel<0, true, false>);

@@ -389,10 +389,6 @@ __global__ void __launch_bounds__(32 * kRedSeg) wgrad_reduce_kernel(const float*
 
 }  // namespace tcw
 
-int wgrad_tma_supported(int64_t m, int64_t k1, int64_t k2, int64_t n);
-int launch_wgrad_tma(const GemmTnArgs& a, int grid, float* partials, int64_t partial_stride, float* colsum_part,
-                     int64_t colsum_stride, cudaStream_t s);
-
 int wgrad_tcgen05_supported(int64_t m, int64_t k1, int64_t k2, int64_t n, uint32_t flags) {
   if (!(flags & MPGNN_F_TF32X3)) return 0;
   if (m < 1 || !(n == 64 || n == 128)) return 0;
@@ -448,14 +444,10 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   const bool masked = a.b_actmask != nullptr;
   const bool stacked = a.k1 == tcw::kFeat / 2;
   const bool single = a.k1 == tcw::kFeat && a.k2 == 0;
-  // MPGNN_WGRAD_TMA=1: the experimental TMA-fed kernel for the 128-wide layers (wgrad_tma_tcgen05.cu), for A/B runs
-  static const bool use_tma = getenv("MPGNN_WGRAD_TMA") != nullptr;
   if (single) {
     if (masked) MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, false, true>));
     else MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, false, true>));
-  } else if (use_tma && wgrad_tma_supported(a.m, a.k1, a.k2, a.n))
-    MPGNN_PROPAGATE(launch_wgrad_tma(a, grid, p.partials, 2 * tcw::kFeat * a.n, p.colsum_part, tcw::kRowsPerChunk * a.n, s));
-  else
+  } else
   switch ((a.n == 128 ? 4 : 0) + (masked ? 2 : 0) + (stacked ? 1 : 0)) {
     case 0: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, false, false>)); break;
     case 1: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, false, true>)); break;

@@ -213,87 +213,6 @@ def test_projection_pipeline_is_race_free_exact_operand_check(n, f_in, f_out):
         assert float((y - want_h).abs().max()) <= 1e-5 * 8, "h operand corrupted in trial %d" % trial
 
 
-def test_experimental_tma_wgrad_matches_default_kernel():
-    """MPGNN_WGRAD_TMA=1 (read once per process, hence the subprocess) selects the TMA-fed weight-gradient kernel;
-    it must agree with the default one and with the fp32 path."""
-    import os
-    import subprocess
-    import sys
-    code = r'''
-import sys, torch
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
-import mpgnn_b200
-from mpgnn_b200 import _lib
-import test_gpu_tcgen05 as t
-n, f = 30001, 128
-ei, et = t._graph(n, 5 * n, 2, seed=11)
-gen = torch.Generator().manual_seed(5)
-x = torch.randn(n, f, generator=gen).cuda(); gy = torch.randn(n, f, generator=gen).cuda()
-w = (torch.randn(f, f, generator=gen) * 0.1).cuda(); root = (torch.randn(f, f, generator=gen) * 0.1).cuda()
-b = torch.zeros(f).cuda()
-graph = mpgnn_b200.RelationGraph(ei, et, n, 2, device="cuda")
-fl = _lib.F_RELU | _lib.F_DROPOUT_SEED | _lib.F_TF32X3
-am = torch.empty(n, f // 32, dtype=torch.int32, device="cuda")
-h, y = t._fwd(graph, 1, x, w, root, b, fl, None, actmask=am)
-g = t._bwd(graph, 1, x, h, None, gy, w, root, fl, actmask=am)
-torch.save([v.cpu() for v in g], sys.argv[1])
-'''
-    outs = []
-    for tag, env in (("ldg", {}), ("tma", {"MPGNN_WGRAD_TMA": "1"})):
-        path = "/tmp/wgrad_%s.pt" % tag
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, **env),
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        outs.append(torch.load(path))
-    for a, c in zip(*outs):
-        assert rel_err(a, c) < TOL
-    assert not torch.equal(outs[0][1], outs[1][1])          # a different kernel did run (other summation order)
-
-
-def test_cta_pair_projection_matches_default_kernel():
-    """MPGNN_PROJ_PAIR=1 (read once per process, hence the subprocess) runs the K > 128 projection on CTA pairs
-    (tcgen05 cta_group::2, one A conversion for all 128 output columns): same numbers as the single-CTA kernel,
-    and the exact-operand stress on top."""
-    import os
-    import subprocess
-    import sys
-    code = r'''
-import sys, torch
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
-import mpgnn_b200
-from mpgnn_b200 import _lib
-import test_gpu_tcgen05 as t
-outs = []
-for n, f_in, f_out in ((30001, 128, 128), (70000, 96, 128), (257, 128, 256)):
-    ei, et = t._graph(n, 5 * n, 2, seed=n)
-    gen = torch.Generator().manual_seed(n)
-    x = torch.randn(n, f_in, generator=gen).cuda()
-    w = (torch.randn(f_in, f_out, generator=gen) * 0.1).cuda(); root = (torch.randn(f_in, f_out, generator=gen) * 0.1).cuda()
-    b = (torch.randn(f_out, generator=gen) * 0.1).cuda()
-    graph = mpgnn_b200.RelationGraph(ei, et, n, 2, device="cuda")
-    fl = _lib.F_RELU | _lib.F_DROPOUT_SEED | _lib.F_TF32X3
-    am = torch.empty(n, f_out // 32, dtype=torch.int32, device="cuda")
-    h, y = t._fwd(graph, 1, x, w, root, b, fl, None, actmask=am)
-    outs += [y.cpu(), am.cpu()]
-    xi = torch.randint(-8, 9, (n, f_in), generator=gen).float().cuda()
-    sel = torch.zeros(f_in, f_out, device="cuda"); sel[torch.arange(f_out, device="cuda") % f_in, torch.arange(f_out, device="cuda")] = 1.0
-    for trial in range(4):
-        _, yi = t._fwd(graph, 1, xi, torch.zeros_like(sel), sel, torch.zeros(f_out, device="cuda"), _lib.F_TF32X3, None)
-        assert torch.equal(yi, xi[:, torch.arange(f_out, device="cuda") % f_in]), (n, f_in, f_out, trial)
-torch.save(outs, sys.argv[1])
-'''
-    res = []
-    for tag, env in (("single", {}), ("pair", {"MPGNN_PROJ_PAIR": "1"})):
-        path = "/tmp/proj_%s.pt" % tag
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, **env),
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-        res.append(torch.load(path))
-    for a, c in zip(*res):
-        if a.dtype == torch.int32:
-            assert (a != c).float().mean() < 1e-4          # the bitmask may differ where y is ~0 in one of the two
-        else:
-            assert rel_err(a, c) < TOL
-
-
 def _classes_of(fn):
     """Kernel classes (ScopedTimer names) the library recorded while `fn` ran."""
     lib = _lib.load()
