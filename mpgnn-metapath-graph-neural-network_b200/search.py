@@ -819,9 +819,10 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
         mine.append([float(i), done[key]])
     gathered = comm.allgather_records(mine, 2, max(1, len(final_metapaths_list)))
     final_dict = {} if final_dict is None else final_dict
-    for part in gathered:                                                    # rank order; later keys overwrite
-        for i, f1 in part:
-            final_dict[str(final_metapaths_list[int(i)])] = f1
+    # inserted in LIST order whatever the assignment and the number of ranks were (the reference's contiguous blocks in
+    # rank order are exactly that): the insertion order breaks ties in final_selection's stable sort; later keys overwrite
+    for i, f1 in sorted((int(i), f1) for part in gathered for i, f1 in part):
+        final_dict[str(final_metapaths_list[i])] = f1
     if log:
         log("candidates: %s" % {k: round(v, 6) for k, v in final_dict.items()})
     # ---- final selection (rank 0 in the reference; replicated here, it is deterministic) ----

@@ -369,6 +369,7 @@ def run_bag_restart_arrays(graph, rel, prob, x_dev, weights, lin, grad_mask, use
     trained weights [N], linear weight [F], best destination per bag, (prediction - label) per bag, value per source [N])."""
     lib = _lib.load()
     dev = graph.device
+    x_dev = x_dev.contiguous()          # the kernel reads row-major [N, F] (a host array may arrive column-major)
     n, feat = graph.num_nodes, x_dev.size(1)
     nb = prob.n_bags
     src = prob.bag_flat.to(torch.int32).contiguous()

@@ -93,7 +93,7 @@ def test_device_pipeline_bag_scorer_matches_reference_golden(fx3, rel0):
     dev = torch.device("cuda")
     sg = sd.SearchGraph(fx3["edge_index"], fx3["edge_type"], fx3["x"].size(0), dev)
     graph = search._graph_of(data, dev)
-    x_dev = fx3["x"].to(dev)
+    x_dev = fx3["x"].to(dev).contiguous()
     lab = fx3["labels"].float().to(dev)
     state = sd.step0_state(sg, rel0, lab, [], "synthetic")
     sd.create_bags(sg, state)
