@@ -40,7 +40,8 @@ using namespace tc;
 
 constexpr int kRowsPerChunk = 32;                 // node rows (MMA K) per pipeline stage
 constexpr int kFeat = 128;                        // feature width of A1 / A2 (MMA M)
-constexpr int kStagesW = 2;
+constexpr int kStagesPair = 2;                     // two A operands: 96 KB per stage
+constexpr int kStagesSingle = 3;                   // one A operand: 64 KB per stage
 constexpr int kProducerWarpsW = 16;
 constexpr int kEpiWarpsW = 4;
 constexpr int kMmaWarpW = kProducerWarpsW + kEpiWarpsW;           // 20
@@ -92,9 +93,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
   constexpr bool kSwap = (N == 128) && !kStacked;      // g_z^T as the M operand, [h | x] as one N = 256 operand
   static_assert(!kSingle || kSwap, "single-operand variant exists for the swapped 128-wide shape only");
   constexpr int kHxWidth = kSingle ? kFeat : 2 * kFeat;   // width of the [h | x] (or lone) N operand
+  // a lone operand needs 64 KB per stage instead of 96: three stages fit, and the producers (what bounds this kernel)
+  // get one more chunk of slack against the MMA warp
+  constexpr int kStagesW = kSingle ? kStagesSingle : kStagesPair;
+  constexpr int kAOps = kSingle ? 1 : 2;                  // A operands staged per chunk
+  constexpr int kLoOff = kSingle ? kATileBytes : 2 * kATileBytes;    // swapped roles: lo image of the [h | x] tile
+  constexpr int kBOff = 2 * kAOps * kATileBytes;          // B tiles follow the A tiles
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b_tile_bytes = kRowsPerChunk * N * 4;                    // one of hi / lo
-  const int stage_bytes = 4 * kATileBytes + 2 * b_tile_bytes;        // a1 hi/lo, a2 hi/lo, b hi/lo
+  const int stage_bytes = kBOff + 2 * b_tile_bytes;                  // a1 hi/lo, (a2 hi/lo,) b hi/lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * stage_bytes);
   // bars: full[kStagesW], empty[kStagesW], done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesW + 1);
@@ -199,8 +206,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         if (kSwap) {
-          split_store(st + a_soff[u], 2 * kATileBytes, src[u]);                    // [h | x] tile: hi @0, lo @32K
-          if (!kSingle) split_store(st + a2_soff[u], 2 * kATileBytes, src[2 + u]);
+          split_store(st + a_soff[u], kLoOff, src[u]);                             // [h | x] tile: hi @0, lo @32K (lone: @16K)
+          if (!kSingle) split_store(st + a2_soff[u], kLoOff, src[2 + u]);
         } else {
           split_store(st + a_soff[u], kATileBytes, src[u]);                        // a1: hi @0, lo @16K
           if (!kStacked) split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
             b.z = (nib & 4u) ? b.z * p.b_scale : 0.f;
             b.w = (nib & 8u) ? b.w * p.b_scale : 0.f;
           }
-          split_store(st + 4 * kATileBytes + b_soff[u], b_tile_bytes, b);          // b: hi, lo
+          split_store(st + kBOff + b_soff[u], b_tile_bytes, b);                    // b: hi, lo
           csum[u].x += b.x; csum[u].y += b.y; csum[u].z += b.z; csum[u].w += b.w;
         }
       }
@@ -267,8 +274,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
           if (kSwap) {
             const uint32_t hx_sbo = (kHxWidth / 32) * 512;
             const uint32_t go = kg * 2 * b_sbo, ho = kg * 2 * hx_sbo;
-            const uint64_t gh = desc_mn(st + 4 * kATileBytes + go, b_sbo), gl = desc_mn(st + 4 * kATileBytes + b_tile_bytes + go, b_sbo);
-            const uint64_t hh = desc_mn(st + ho, hx_sbo), hl = desc_mn(st + 2 * kATileBytes + ho, hx_sbo);
+            const uint64_t gh = desc_mn(st + kBOff + go, b_sbo), gl = desc_mn(st + kBOff + b_tile_bytes + go, b_sbo);
+            const uint64_t hh = desc_mn(st + ho, hx_sbo), hl = desc_mn(st + kLoOff + ho, hx_sbo);
             const uint32_t idesc_t = make_idesc_mn(N, kHxWidth);
             const uint32_t acc_t = (it | kg) != 0 ? 1u : 0u;
             umma_tf32(tmem_base, gh, hh, idesc_t, acc_t);
@@ -280,8 +287,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
           const uint64_t a1h = desc_mn(st + ao, a_sbo), a1l = desc_mn(st + kATileBytes + ao, a_sbo);
           const uint64_t a2h = desc_mn(st + 2 * kATileBytes + ao, a_sbo);
           const uint64_t a2l = desc_mn(st + 3 * kATileBytes + ao, a_sbo);
-          const uint64_t bh = desc_mn(st + 4 * kATileBytes + bo, b_sbo);
-          const uint64_t bl = desc_mn(st + 4 * kATileBytes + b_tile_bytes + bo, b_sbo);
+          const uint64_t bh = desc_mn(st + kBOff + bo, b_sbo);
+          const uint64_t bl = desc_mn(st + kBOff + b_tile_bytes + bo, b_sbo);
           const uint32_t acc = (it | kg) != 0 ? 1u : 0u;
           umma_tf32(tmem_base, a1h, bh, idesc, acc);
           umma_tf32(tmem_base, a1l, bh, idesc, 1u);
@@ -429,8 +436,10 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   p.b_actmask = a.b_actmask; p.b_scale = a.b_scale;
   p.partials = ws;
   p.colsum_part = ws + (int64_t)grid * 2 * tcw::kFeat * a.n;
-  const size_t smem = (size_t)tcw::kStagesW * (4 * tcw::kATileBytes + 2 * tcw::kRowsPerChunk * a.n * 4) +
-                      (2 * tcw::kStagesW + 1) * 8 + 16;
+  const bool single_op = a.k1 == tcw::kFeat && a.k2 == 0;
+  const int n_stages = single_op ? tcw::kStagesSingle : tcw::kStagesPair;
+  const size_t smem = (size_t)n_stages * ((single_op ? 2 : 4) * tcw::kATileBytes + 2 * tcw::kRowsPerChunk * a.n * 4) +
+                      (2 * n_stages + 1) * 8 + 16;
   auto launch = [&](auto kernel) -> int {
     // the opt-in limit is per function and process wide: always raise it to the device maximum, so that concurrent
     // launches of the same kernel with different tile sizes (candidate trainers on several host threads) cannot
