@@ -402,7 +402,7 @@ def main(args):
     if results:
         f_meta, test_f1 = search.final_selection(final_dict, search.make_union_fn(
             data_mpgnn, input_dim, args.hidden_dim, tot_rel, args.hidden_dim, ll_output_dim,
-            epochs=getattr(args, "epochs", None)))
+            epochs=getattr(args, "epochs", None)), comm)
     for res in results:
         res["final_meta"], res["test_f1"] = f_meta, test_f1
     if comm.rank == 0:

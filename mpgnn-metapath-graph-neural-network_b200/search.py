@@ -552,15 +552,23 @@ def gap_select_step0(relations, losses):
     return list(relations)
 
 
-def final_selection(final_dict, train_union_fn):
+def final_selection(final_dict, train_union_fn, comm=None):
     """main.py:1463-1476: stable sort by validation F1 (desc), top 3, then add metapaths to the union
-    while the test F1 strictly improves."""
+    while the test F1 strictly improves.  The unions the rule can ask for are known in advance (the prefixes of the
+    top 3) and each one's score does not depend on the others, so with several ranks prefix i is trained by rank
+    i mod size, the scores are exchanged and the rule is applied to them -- same result, one training deep instead of
+    up to three (rank 0 alone does this stage in the reference)."""
     ordered = sorted(final_dict.items(), key=lambda item: item[1], reverse=True)[:3]
+    metas = [[int(v) for v in key.strip("[]").split(",") if v.strip()] for key, _ in ordered]
+    scores = None
+    if comm is not None and comm.size > 1 and len(metas) > 1:
+        mine = [[float(i), float(train_union_fn([list(m) for m in metas[:i + 1]]))]
+                for i in range(len(metas)) if i % comm.size == comm.rank]
+        scores = dict((int(i), f1) for part in comm.allgather_records(mine, 2, len(metas)) for i, f1 in part)
     test_meta, f_meta, old = [], [], 0.0
-    for key, _ in ordered:
-        meta = [int(v) for v in key.strip("[]").split(",") if v.strip()]
+    for i, meta in enumerate(metas):
         test_meta.append(meta)
-        f1 = train_union_fn(list(test_meta))
+        f1 = scores[i] if scores is not None else train_union_fn(list(test_meta))
         if f1 > old:
             old = f1
             f_meta.append(meta)
@@ -694,6 +702,25 @@ class _DevicePipeline:
         return self.sd.accept_relation(self.sg, st, int(rel), lin, torch.cat([vals, vals_r]), visited, self.x_dev,
                                        self.dataset)
 
+    def share_state(self, st, owner, comm):
+        """Broadcast of a BagState from the rank that computed it (a few MB of int32/float32 over NVLink; the only
+        tensor traffic of the search, replacing a re-scoring of the accepted relation on every other rank)."""
+        dev = self.device if comm.dist.get_backend() == "nccl" else torch.device("cpu")
+        head = torch.zeros(2, dtype=torch.int64, device=dev)
+        if st is not None:
+            head[0], head[1] = int(st.rel), int(st.src_order.numel())
+        comm.dist.broadcast(head, src=owner)
+        rel, n_src = int(head[0]), int(head[1])
+        n = self.sg.n
+        parts = [("src_order", torch.int64, n_src), ("count0", torch.int32, n), ("count1", torch.int32, n),
+                 ("labels", torch.float32, n)]
+        got = {}
+        for name, dt, cnt in parts:
+            t = getattr(st, name).to(device=dev, dtype=dt).contiguous() if st is not None else torch.empty(cnt, dtype=dt, device=dev)
+            comm.dist.broadcast(t, src=owner)
+            got[name] = t.to(self.device)
+        return self.sd.BagState(rel, got["src_order"], got["count0"], got["count1"], got["labels"])
+
 
 def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, ll_output_dim, dataset, comm=None,
                   score_fn=None, eval_fn=None, union_fn=None, bag_score_fn=None, log=None, max_depth=3,
@@ -784,6 +811,7 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
                 if log:
                     log("depth %d meta %s: relations %s losses %s accepted %s" % (
                         k + 1, meta, steps[-1]["relations"], ["%.5f" % l for l in steps[-1]["losses"]], accepted))
+                owner = {int(r_): q for q in range(comm.size) for r_ in relation_split(rels_k, comm.size, q)}
                 for rel, loss in result_k:
                     if rel not in accepted:
                         continue
@@ -791,7 +819,13 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
                     intermediate.append(tmp_meta)
                     if tmp_meta not in final_metapaths_list:
                         final_metapaths_list.append(tmp_meta)
-                    state[str(tmp_meta)] = pipe.accept(st, rel, len(meta), cache.get(rel))
+                    if comm.size > 1 and hasattr(pipe, "share_state"):
+                        # the rank that scored the relation holds its restarts: it alone retrains / relabels / cleans and
+                        # hands the new (array) state to the others, instead of every rank re-scoring it
+                        new = pipe.accept(st, rel, len(meta), cache.get(rel)) if comm.rank == owner[rel] else None
+                        state[str(tmp_meta)] = pipe.share_state(new, owner[rel], comm)
+                    else:
+                        state[str(tmp_meta)] = pipe.accept(st, rel, len(meta), cache.get(rel))
             current_metapaths_list = [list(m) for m in intermediate]
     if torch.cuda.is_available():
         torch.cuda.synchronize()
@@ -829,7 +863,7 @@ def greedy_search(data, data_mpgnn, input_dim, hidden_dim, num_rel, output_dim, 
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     t_eval = time.time()
-    f_meta, test_f1 = final_selection(final_dict, union_fn) if select else (None, None)
+    f_meta, test_f1 = final_selection(final_dict, union_fn, comm) if select else (None, None)
     if log and select:
         log("final meta: %s test acc: %s" % (f_meta, test_f1))
     if timings is not None:
