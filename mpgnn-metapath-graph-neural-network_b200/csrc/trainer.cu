@@ -127,11 +127,19 @@ struct Trainer {
   bool params_set;           // run()/evaluate() refuse to work on the recycled slab's stale bytes
 };
 
+// split-K partials of the head's two weight gradients: [gW2t; gb2] = a1^T glg (H+1 x C) and [gW1t; gb1] = E^T g_z1
+// (cat+1 x H).  The split is a function of the shape and NOT monotone in it (thin outputs get more, shorter row
+// ranges), so the buffer is sized from the shapes actually launched.
+static int64_t trainer_tn_floats(const Trainer& t) {
+  const int64_t a = gemm_tn_partial_floats(t.n, t.hidden + 1, t.classes);
+  const int64_t b = gemm_tn_partial_floats(t.n, t.cat + 1, t.hidden);
+  return a > b ? a : b;
+}
+
 static int64_t trainer_ws_bytes(const Trainer& t) {
   int64_t a = hop_workspace_bytes(t.n, t.f_in, t.hidden), b = hop_workspace_bytes(t.n, t.hidden, t.hidden);
   int64_t hop = a > b ? a : b;
-  int64_t kmax = t.cat > t.classes ? t.cat : t.classes;
-  int64_t tn = gemm_tn_partial_floats(t.n, kmax + 1, kmax) * 4 + 4096;
+  int64_t tn = trainer_tn_floats(t) * 4 + 4096;
   return (hop > tn ? hop : tn) + 1024 * 8;
 }
 
@@ -382,8 +390,7 @@ static int trainer_backward(Trainer* t, cudaStream_t s) {
   const int64_t n = t->n, H = t->hidden, C = t->classes, K1 = t->cat;
   const float* emb = t->n_paths > 1 ? t->emb : t->y[t->n_layers - 1];
   Workspace ws(t->ws, t->ws_bytes);
-  const int64_t kmax = K1 > C ? K1 : C;
-  const int64_t pf = gemm_tn_partial_floats(n, kmax + 1, kmax);
+  const int64_t pf = trainer_tn_floats(*t);
   float* partials = ws.take<float>(pf);
   MPGNN_REQUIRE(partials != nullptr, MPGNN_EINVAL, "trainer: workspace too small");
   // fc2: [gW2t; gb2] = a1^T glg

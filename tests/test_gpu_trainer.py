@@ -283,3 +283,33 @@ def test_trainer_requires_parameters_and_valid_labels(fx3):
     torch.manual_seed(30)
     tr9.load_state_dict(mpgnn_b200.MPNetm(2, 64, 4, 64, 2, 1, [[9, 0]], device="cpu").state_dict())
     assert np.isfinite(tr9.run(2)[:2]).all()
+
+
+def test_trainer_union_of_three_metapaths_on_a_large_graph():
+    """The final selection trains unions of up to three metapaths (main.py:1465-1475) at the size of the searched graph;
+    the scratch of the head's split-K reductions depends on the shape in a non-monotone way, so this runs one at
+    400k nodes (where round 2's first sizing overflowed) and checks it against the epoch-by-epoch Python path."""
+    gen = torch.Generator().manual_seed(11)
+    n, e, r = 400_000, 1_600_000, 6
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    et = torch.randint(0, r, (e,), generator=gen)
+    x = torch.nn.functional.one_hot(torch.randint(0, 2, (n,), generator=gen), 2).float()
+    y = torch.randint(0, 2, (n,), generator=gen)
+    perm = torch.randperm(n, generator=gen)
+    data = mpgnn_b200.Data(x=x, edge_index=ei, edge_type=et, num_nodes=n, train_idx=perm[:200_000], train_y=y[perm[:200_000]],
+                           val_idx=perm[200_000:300_000], val_y=y[perm[200_000:300_000]], test_idx=perm[300_000:],
+                           test_y=y[perm[300_000:]])
+    metas = [[3], [1, 3], [5, 2, 0]]
+    torch.manual_seed(30)
+    model = mpgnn_b200.MPNetm(2, 64, r, 64, 2, len(metas), metas, device="cpu")
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    tr = mpgnn_b200.CandidateTrainer(data, 2, 64, 2, metas, dropout_p=0.0, max_epochs=3)
+    tr.load_state_dict(sd0)
+    trace = tr.run(3)[:3]
+    assert np.isfinite(trace).all()
+    model.to("cuda")
+    model.dropout.p = model.dropout2.p = 0.0
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0005)
+    for ep in range(3):
+        loss, _ = mpgnn_b200.mpgnn_train(model, opt, data)
+        assert abs(loss - trace[ep, 0]) < 1e-4 * abs(trace[ep, 0]), (ep, loss, trace[ep, 0])
