@@ -555,13 +555,13 @@ def gap_select_step0(relations, losses):
 def final_selection(final_dict, train_union_fn, comm=None):
     """main.py:1463-1476: stable sort by validation F1 (desc), top 3, then add metapaths to the union
     while the test F1 strictly improves.  The unions the rule can ask for are known in advance (the prefixes of the
-    top 3) and each one's score does not depend on the others, so with several ranks prefix i is trained by rank
-    i mod size, the scores are exchanged and the rule is applied to them -- same result, one training deep instead of
-    up to three (rank 0 alone does this stage in the reference)."""
+    top 3) and each one's score does not depend on the others, so with at least as many ranks as prefixes prefix i
+    is trained by rank i, the scores are exchanged and the rule is applied to them -- same result, one training deep
+    instead of up to three (rank 0 alone does this stage in the reference)."""
     ordered = sorted(final_dict.items(), key=lambda item: item[1], reverse=True)[:3]
     metas = [[int(v) for v in key.strip("[]").split(",") if v.strip()] for key, _ in ordered]
     scores = None
-    if comm is not None and comm.size > 1 and len(metas) > 1:
+    if comm is not None and len(metas) > 1 and comm.size >= len(metas):       # one prefix per rank, or not at all
         mine = [[float(i), float(train_union_fn([list(m) for m in metas[:i + 1]]))]
                 for i in range(len(metas)) if i % comm.size == comm.rank]
         scores = dict((int(i), f1) for part in comm.allgather_records(mine, 2, len(metas)) for i, f1 in part)
