@@ -384,3 +384,55 @@ def test_lpt_assignment_covers_every_position_once_and_balances():
     load = [sum(len(m) for m in {tuple(metas[i]) for i in p}) for p in two]
     assert abs(load[0] - load[1]) <= 1
     assert search.lpt_assignment(metas, 2) == two           # deterministic
+
+
+def _worker3(rank, size, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(size))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import types
+    import torch.distributed as dist
+    from mpgnn_b200 import search_device as sd
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    comm = search.Comm()
+    # (a) final selection with a rank per prefix: same result and the same three unions as the sequential rule
+    calls = []
+
+    def union(metas):
+        calls.append([list(m) for m in metas])
+        return {1: 0.8, 2: 0.9, 3: 0.9}[len(metas)]
+
+    fm, f1 = search.final_selection({"[1]": 0.7, "[2, 0]": 0.9, "[3]": 0.9, "[4]": 0.1}, union, comm)
+    # (b) the state of an accepted relation travels from the rank that computed it
+    pipe = object.__new__(search._DevicePipeline)
+    pipe.device, pipe.sd, pipe.sg = torch.device("cpu"), sd, types.SimpleNamespace(n=50)
+    owner = 2
+    st = None
+    if rank == owner:
+        st = sd.BagState(7, torch.arange(3, 20, 2), torch.arange(50, dtype=torch.int32) % 3,
+                         torch.arange(50, dtype=torch.int32) % 5, (torch.arange(50) % 2).float())
+    got = pipe.share_state(st, owner, comm)
+    q.put((rank, fm, f1, calls, got.rel, got.src_order.tolist(), got.count0.tolist(), got.count1.tolist(), got.labels.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_3_gloo_final_selection_and_state_broadcast():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker3, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    results = {r[0]: r[1:] for r in (q.get(timeout=120) for _ in range(3))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(3):
+        fm, f1, calls, rel, src, c0, c1, lab = results[r]
+        assert fm == [[2, 0], [3]] and f1 == 0.9                       # the sequential rule's answer (test above)
+        assert calls == [[[2, 0]], [[2, 0], [3]], [[2, 0], [3], [1]]][r:r + 1]      # rank r trained prefix r, nothing else
+        assert rel == 7 and src == list(range(3, 20, 2))
+        assert c0 == [i % 3 for i in range(50)] and c1 == [i % 5 for i in range(50)] and lab == [float(i % 2) for i in range(50)]
