@@ -305,6 +305,30 @@ def run_ours(args):
     kern = _lib.timing_collect()
     e_r_mean = e_sum / args.steps
 
+    # ---- the same hop through the reference-facing Python call (autograd function over the C ABI) ------------------
+    # conv.hop(...) is what MPNetm.forward calls per layer (model.py:209-214: conv -> relu -> dropout); it allocates its
+    # outputs per call like any torch op.  Reported next to the raw C-ABI time above.
+    api_ms = None
+    if not args.no_api:
+        xg = x.detach().requires_grad_(True)
+
+        def api_hop(step):
+            rel = (step * world + rank) % r
+            xg.grad = None
+            conv.zero_grad(set_to_none=True)
+            out = conv.hop(rel, xg, graph, relu=True, dropout_p=DROPOUT_P, seed=1234, offset=step)
+            out.backward(gy)
+            return graph.relation_edges(rel)
+
+        for s_ in range(2):
+            api_hop(s_)
+        api_steps = max(4, min(args.steps, 16))
+        ms_api, _ = timed(api_hop, api_steps, args.warmup)
+        api_ms = ms_api / api_steps
+        del xg
+        conv.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+
     # ---- end-to-end arm: host (pinned) features in, gradients + a loss scalar out ---------
     e2e = None
     if not args.no_e2e:
@@ -448,6 +472,10 @@ def run_ours(args):
                                                   "note": "SURVEY 8(d) B_fwd + B_bwd without the 8 N F credit for t"},
                                    "as_built": {"bytes": hop_built, "frac": hop_built / step_s / 1e9 / hbm,
                                                 "note": "sum of the per-kernel bytes of the hop as built"}},
+                  "reference_api": None if api_ms is None else {
+                      "ms_per_step": api_ms, "vs_c_abi": api_ms / (ms / args.steps),
+                      "call": "CustomRGCNConv.hop(relation, x, graph, relu=True, dropout_p=0.6) + backward through "
+                              "torch.autograd (outputs allocated per call)"},
                   "h_layout": "compact (one row of h per node with edges of the relation)" if compact else "dense",
                   "mean_rows_with_edges": nnz_mean,
                   "graph_build_s": build_s, "rows_per_s": n * args.steps * world / (ms * 1e-3),
@@ -763,6 +791,7 @@ def main():
                     help="tf32x3 = fp32-parity 3xTF32 split on tcgen05 (default); fp32 = exact-fp32 SIMT projection")
     ap.add_argument("--dense-h", action="store_true", help="keep the aggregated features dense (N rows) instead of compact")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip timing the same hop through the Python layer API")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tenth", action="store_true", help="reference arm: force the 1/10-scale sample")
     ap.add_argument("--no-candidates", action="store_true", help="skip the candidate-scoring (C2 shape) measurement")
