@@ -48,6 +48,11 @@ int mpgnn_abi_version(void);
  * collect() synchronises on the recorded events and returns the number of classes, their
  * ';'-separated names, accumulated milliseconds and call counts. */
 long long mpgnn_launch_count(void);
+/* Upper bound on the CTAs (= SMs) a tensor-core projection launched FROM THE CALLING THREAD may take; 0 = all.  For
+ * callers that run several independent trainings side by side on their own streams (the candidate fan-out of
+ * main.py:1444-1462 on one GPU): persistent one-CTA-per-SM kernels of different streams otherwise serialise.  Results
+ * do not depend on it; CUDA graphs captured while it is set keep the grid they were captured with. */
+void mpgnn_set_tc_cta_cap(int max_ctas);
 void mpgnn_timing_enable(int on);
 void mpgnn_timing_reset(void);
 int mpgnn_timing_collect(char* names, int64_t names_bytes, double* ms, int64_t* calls, int64_t capacity);

@@ -54,6 +54,7 @@ PROTOTYPES = {
                                     _u64, _u32, _i64, _c.POINTER(_ptr)]),
     "mpgnn_trainer_create_multi": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _i64,
                                           _dbl, _u64, _u32, _i64, _c.POINTER(_ptr)]),
+    "mpgnn_set_tc_cta_cap": (None, [_i32]),
     "mpgnn_trainer_free": (None, [_ptr]),
     "mpgnn_trainer_num_params": (_i64, [_ptr]),
     "mpgnn_trainer_set_params": (_i32, [_ptr, _ptr, _ptr]),

@@ -84,6 +84,7 @@ int graph_build_device(const int64_t* d_edge_index, const int64_t* d_edge_type, 
                        cudaStream_t s, mpgnn_graph_impl** out);
 void graph_free(mpgnn_graph_impl* g);
 int64_t hop_workspace_bytes(int64_t n, int64_t f_in, int64_t f_out);
+void set_tc_cta_cap(int cap);
 int hop_h_compact(const mpgnn_graph_impl* g, int64_t rel, int64_t f_in, int64_t f_out, uint32_t flags);
 int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in, const float* w, const float* root,
             const float* bias, int64_t f_out, uint32_t flags, double p, uint64_t seed, uint64_t offset,
@@ -140,6 +141,8 @@ extern "C" {
 const char* mpgnn_last_error(void) { return g_error; }
 
 int mpgnn_abi_version(void) { return 1; }
+
+void mpgnn_set_tc_cta_cap(int max_ctas) { set_tc_cta_cap(max_ctas); }
 
 long long mpgnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

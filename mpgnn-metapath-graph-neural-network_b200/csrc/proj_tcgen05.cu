@@ -563,6 +563,10 @@ static int make_tensor_map(CUtensorMap* map, const float* base, int64_t rows, in
   return MPGNN_OK;
 }
 
+static thread_local int g_tc_cta_cap = 0;
+int tc_cta_cap() { return g_tc_cta_cap; }
+void set_tc_cta_cap(int cap) { g_tc_cta_cap = cap > 0 ? cap : 0; }
+
 static int pick_bn(int64_t k, int64_t n) {
   if (n % 128 == 0 && k * 128 * 8 <= tc::kMaxBBytes) return 128;
   if (n % 64 == 0 && k * 64 * 8 <= tc::kMaxBBytes) return 64;
@@ -641,7 +645,12 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
 #endif
   const int64_t n_tiles = ceil_div(a.m, pair ? 2 * tc::kTileM : tc::kTileM);
   int64_t grid = n_tiles * n_slices;           // work units: CTAs, or clusters of two
-  const int64_t max_units = pair ? kNumSMs / 2 : kNumSMs;
+  int64_t max_units = pair ? kNumSMs / 2 : kNumSMs;
+  // concurrent callers (candidate trainers of one wave, each on its own stream) may ask for a share of the SMs: a
+  // persistent CTA takes a whole SM, so full-width launches of different streams only ever run one after the other.
+  // The result does not depend on the grid (every tile is computed the same way whoever owns it).
+  const int cap = tc_cta_cap();
+  if (cap > 0 && cap < max_units) max_units = cap < n_slices ? n_slices : cap;
   if (grid > max_units) grid = (max_units / n_slices) * n_slices;
   if (pair) grid *= 2;
   const size_t smem = (size_t)2 * k * bnb * 4 + (size_t)tc::kRawStages * tc::kRawBytes +
