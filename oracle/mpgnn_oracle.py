@@ -297,3 +297,45 @@ def score_candidate(sd, data, metapaths, epochs=999, mask_fn=None, return_trace=
     if return_trace:
         return f1_val, sd, trace
     return f1_val
+
+
+# --------------------------------------------------------------------------------------
+# f4: the all-relation comparison model (model.py:132-151 `Net`; main_rgcn.py:452-472)
+# --------------------------------------------------------------------------------------
+
+
+def rgcn_conv_init(in_channels, out_channels, num_relations):
+    """torch_geometric.nn.RGCNConv.reset_parameters (PyG 2.3.1, third-party): glorot(weight [R, in, out]), glorot(root),
+    zeros(bias), in that order from the global torch CPU generator."""
+    w = glorot_(torch.empty(num_relations, in_channels, out_channels))
+    r = glorot_(torch.empty(in_channels, out_channels))
+    return {"weight": w, "root": r, "bias": torch.zeros(out_channels)}
+
+
+def rgcn_conv_forward(x, edge_index, edge_type, weight, root, bias):
+    """RGCNConv.forward without decomposition / pyg_lib: the per-relation loop the reference's CustomRGCNConv was cut
+    down from (mp_rgcn_layer.py:249-258): out = sum_r mean_r(x) @ weight[r] + x @ root + bias."""
+    out = torch.zeros(x.size(0), weight.size(2))
+    for r in range(weight.size(0)):
+        h, _ = propagate_mean(x, masked_edge_index(edge_index, edge_type == r))
+        out = out + h @ weight[r]
+    return out + x @ root + bias
+
+
+def net_init(input_dim, hidden_dim, num_rel, output_dim, ll_output_dim):
+    """Net.__init__ (model.py:133-139): conv1, conv2, LinearLayer in construction order; state_dict keys of the model."""
+    c1 = rgcn_conv_init(input_dim, hidden_dim, num_rel)
+    c2 = rgcn_conv_init(hidden_dim, output_dim, num_rel)
+    lin = torch.nn.Linear(output_dim, ll_output_dim)
+    sd = {"conv1." + k: v for k, v in c1.items()}
+    sd.update({"conv2." + k: v for k, v in c2.items()})
+    sd.update({"LinearLayer.weight": lin.weight.detach().clone(), "LinearLayer.bias": lin.bias.detach().clone()})
+    return sd
+
+
+def net_forward(sd, x, edge_index, edge_type, metapath_length):
+    """Net.forward (model.py:141-150): relu(conv1), then relu(conv2) metapath_length - 1 times, LinearLayer, log_softmax."""
+    for layer in range(metapath_length):
+        p = "conv1." if layer == 0 else "conv2."
+        x = torch.relu(rgcn_conv_forward(x, edge_index, edge_type, sd[p + "weight"], sd[p + "root"], sd[p + "bias"]))
+    return torch.log_softmax(x @ sd["LinearLayer.weight"].t() + sd["LinearLayer.bias"], dim=1)

@@ -156,3 +156,21 @@ def test_macro_f1_matches_sklearn():
             assert orc.macro_f1(p, t) == pytest.approx(f1_score(p, t, average="macro"), abs=1e-12)
     assert orc.macro_f1(np.zeros(10, int), np.zeros(10, int)) == 1.0
     assert orc.macro_f1(np.zeros(10, int), np.ones(10, int)) == 0.0
+
+
+def test_rgcn_baseline_oracle_matches_reference_golden():
+    """f4: the oracle's restatement of `Net` / PyG's RGCNConv against the golden recorded from the unmodified
+    model.py behind the stand-ins (tests/golden/make_golden_rgcn.py): same draws, same log-probabilities."""
+    import torch
+    from conftest import fixture_as_torch, load_golden
+    from oracle import mpgnn_oracle as orc
+    g = load_golden("rgcn_len3")
+    fx = fixture_as_torch("fixture_len3")
+    torch.manual_seed(30)
+    sd = orc.net_init(2, 64, fx["num_relations"], 64, 2)
+    for k, v in sd.items():
+        assert torch.equal(v, torch.from_numpy(g["sd0." + k])), k
+    for length, key in ((2, "eval_logp"), (3, "eval_logp_len3")):
+        logp = orc.net_forward(sd, fx["x"], fx["edge_index"], fx["edge_type"], length)
+        ref = torch.from_numpy(g[key])
+        assert float((logp - ref).abs().max()) <= 1e-6 * float(ref.abs().max()), key

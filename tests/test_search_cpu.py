@@ -436,3 +436,31 @@ def test_world_size_3_gloo_final_selection_and_state_broadcast():
         assert calls == [[[2, 0]], [[2, 0], [3]], [[2, 0], [3], [1]]][r:r + 1]      # rank r trained prefix r, nothing else
         assert rel == 7 and src == list(range(3, 20, 2))
         assert c0 == [i % 3 for i in range(50)] and c1 == [i % 5 for i in range(50)] and lab == [float(i % 2) for i in range(50)]
+
+
+def test_final_dict_is_shared_across_one_vs_rest_label_sets():
+    """main.py:1208 creates `final_dict` once, before the loop over the one-vs-rest label sets (a 3-class label file
+    gives three of them, main.py:161-172), every label set's candidates are merged into it (a repeated metapath is
+    overwritten by the later label set) and the top-3 / greedy-union selection runs ONCE after the loop
+    (main.py:1463-1476) -- what mpgnn_b200.main.main() does with `greedy_search(..., final_dict=shared, select=False)`."""
+    fx = fixture_as_torch("fixture_len3")
+    three_class = (fx["labels"] + (torch.arange(fx["labels"].numel()) % 3 == 0).long()).clamp(max=2)       # classes 0, 1, 2
+    binary_sets = [(three_class == c).long() for c in range(3)]
+    shared, unions, per_set = {}, [], []
+    for c, lab in enumerate(binary_sets):
+        data = mpgnn_b200.Data(x=fx["x"], edge_index=fx["edge_index"], edge_type=fx["edge_type"], labels=lab.unsqueeze(-1),
+                               num_nodes=fx["x"].size(0), source_nodes_mask=[])
+        res = search.greedy_search(data, None, 2, 64, 4, 64, 2, "synthetic", comm=search.Comm(),
+                                   score_fn=lambda d, rel: 0.01 * (int(rel) + 1),            # one gap at most: all kept
+                                   eval_fn=lambda meta, c=c: 0.3 + 0.1 * c + 0.01 * meta[0],
+                                   union_fn=lambda metas: unions.append(metas) or 0.5, final_dict=shared, select=False)
+        assert res["final_meta"] is None and res["final_dict"] is shared
+        per_set.append(set(str([r]) for r in res["kept"]))
+    assert not unions                                               # nothing selected inside the loop
+    assert set(shared) == set().union(*per_set)
+    for key in shared:                                              # the LAST label set that produced a key wins
+        last = max(c for c in range(3) if key in per_set[c])
+        assert shared[key] == pytest.approx(0.3 + 0.1 * last + 0.01 * int(key.strip("[]")))
+    f_meta, f1 = search.final_selection(shared, lambda metas: unions.append([list(m) for m in metas]) or 0.5)
+    best = sorted(shared.items(), key=lambda kv: kv[1], reverse=True)[0][0]
+    assert f_meta == [[int(best.strip("[]"))]] and f1 == 0.5 and len(unions) == 2          # second union did not improve
