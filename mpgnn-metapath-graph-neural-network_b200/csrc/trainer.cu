@@ -352,7 +352,7 @@ static int trainer_forward(Trainer* t, bool train, cudaStream_t s) {
     for (int l = t->path_off[i]; l < t->path_off[i + 1]; ++l) {
       const bool first = l == t->path_off[i];
       const int64_t fi = first ? t->f_in : H;
-      uint32_t fl = MPGNN_F_RELU | (t->flags & MPGNN_F_TF32X3);
+      uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_COMPACT_H | MPGNN_F_DENSE_H));
       if (train && t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
       MPGNN_PROPAGATE(hop_fwd(t->g, t->rel[l], in, fi, t->params + t->off_w[l], t->params + t->off_root[l],
                               t->params + t->off_bias[l], H, fl, t->dropout_p, t->seed, 0, nullptr, t->h[l], t->y[l],
@@ -437,7 +437,7 @@ static int trainer_backward(Trainer* t, cudaStream_t s) {
       const bool first = l == t->path_off[i];
       const int64_t fi = first ? t->f_in : H;
       const float* in = first ? t->x : t->y[l - 1];
-      uint32_t fl = MPGNN_F_RELU | (t->flags & MPGNN_F_TF32X3);
+      uint32_t fl = MPGNN_F_RELU | (t->flags & (MPGNN_F_TF32X3 | MPGNN_F_COMPACT_H | MPGNN_F_DENSE_H));
       if (t->dropout_p > 0.0) fl |= MPGNN_F_DROPOUT_SEED;
       if (!first) fl |= MPGNN_F_NEED_GX;
       MPGNN_PROPAGATE(hop_bwd(t->g, t->rel[l], in, t->h[l], t->y[l], reinterpret_cast<const uint32_t*>(t->am[l]), gy, fi,

@@ -107,7 +107,7 @@ def mpgnn_train(model, optimizer, data):
     loss = F.nll_loss(out[st["train_idx"]].squeeze(-1), st["train_y"])
     loss.backward()
     optimizer.step()
-    return float(loss), weights
+    return float(loss.detach()), weights
 
 
 @torch.no_grad()
@@ -141,7 +141,7 @@ class CandidateTrainer:
     mpgnn_parallel_multiple_x trains for the final selection, model.py:203-220)."""
 
     def __init__(self, data_mpgnn, input_dim, hidden_dim, ll_output_dim, metapath, device=None, dropout_p=0.6,
-                 seed=None, precision="tf32x3", max_epochs=EPOCHS_PER_CANDIDATE):
+                 seed=None, precision="tf32x3", max_epochs=EPOCHS_PER_CANDIDATE, h_layout="auto"):
         lib = _lib.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if len(metapath) and isinstance(metapath[0], (int, np.integer)):
@@ -157,6 +157,7 @@ class CandidateTrainer:
         if precision not in ("tf32x3", "fp32"):
             raise ValueError("precision must be 'fp32' or 'tf32x3'")
         flags = _lib.F_TF32X3 if precision == "tf32x3" else 0
+        flags |= {"auto": 0, "compact": _lib.F_COMPACT_H, "dense": _lib.F_DENSE_H}[h_layout]     # see CustomRGCNConv.hop
         rel = np.asarray([r for mp in self.metapaths for r in mp], dtype=np.int64)
         path_ptr = np.cumsum([0] + [len(mp) for mp in self.metapaths]).astype(np.int64)
         handle = ctypes.c_void_p()
