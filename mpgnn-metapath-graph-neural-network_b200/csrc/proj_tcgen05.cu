@@ -124,11 +124,21 @@ __global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, 
 // MMA thread issues M256 x N(BN) x K8 MMAs that read both halves -- for K = 256 (forward) this is what lets one pass
 // over A produce all 128 output columns instead of two CTAs converting the same tile for 64 columns each.
 // kAdd: the epilogue adds rows of a compact matrix (the compact hop: y = act(x root + b + scatter(h_c W))).
-template <int kDrop, bool kDeg, bool kMasked, bool kPair = false, bool kAdd = false>
+// kWide (with kAdd): 8 converter warps (one group) and 16 epilogue warps instead of 16 + 8.  The forward's epilogue
+// (bias, relu, dropout bits, bitmask, compact addend) executes ~620 instructions per 32x32 block against ~120 for a
+// converter's block: with 8 epilogue warps each one ran ~1240 instructions per tile, stalled on latencies 7/8 of the
+// time, and the whole pipeline backed up behind them.  Every wide epilogue warp owns 16 columns of two chunks per tile
+// (half the latency chain) and a 2 KB staging tile stored with 16-column TMA boxes.
+template <int kDrop, bool kDeg, bool kMasked, bool kPair = false, bool kAdd = false, bool kWide = false>
 __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_a1,
                                                                    const __grid_constant__ CUtensorMap tmap_a2,
                                                                    const __grid_constant__ CUtensorMap tmap_out,
                                                                    const __grid_constant__ CUtensorMap tmap_out2) {
+  static_assert(!kWide || (kAdd && !kPair && !kDeg && !kMasked), "the wide-epilogue variant exists for the compact forward only");
+  constexpr int kProd = kWide ? kConvGroupWarps : kProducerWarps;    // converter warps: 8 or 16
+  constexpr int kGroups = kProd / kConvGroupWarps;                   // converter groups taking alternate chunks: 1 or 2
+  constexpr int kEpi = kMmaWarp - kProd;                             // epilogue warps: 16 or 8
+  constexpr int kStg = kWide ? kStgBytes / 2 : kStgBytes;            // staging tile per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem[];
   const int K = p.k1 + p.k2;
   const int BN = p.bn;                                    // accumulator width
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   uint8_t* sm_b_lo = smem + b_bytes;
   uint8_t* sm_raw = smem + 2 * b_bytes;                   // kRawStages raw chunks, 1024-byte aligned (swizzle)
   uint8_t* sm_stg = sm_raw + kRawStages * kRawBytes;                            // kEpiWarps staging tiles (1024-aligned)
-  float* sm_bias = reinterpret_cast<float*>(sm_stg + kEpiWarps * kStgBytes);    // BN floats (slice bias)
+  float* sm_bias = reinterpret_cast<float*>(sm_stg + kEpi * kStg);              // BN floats (slice bias)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_bias + 128);
   // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], raw_full[kRawStages], raw_empty[kRawStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kRawStages);
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, kPair ? 2 * kEpiWarps : kEpiWarps);
+      mbar_init(bar_tempty + 8 * b, kPair ? 2 * kEpi : kEpi);
     }
     for (int r = 0; r < kRawStages; ++r) {
       mbar_init(bar_rfull + 8 * r, 1);                 // one arrive.expect_tx + the TMA's byte count
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
   const uint32_t bar_full_l = kPair ? mapa_rank(bar_full, 0) : bar_full;
   const uint32_t bar_tempty_l = kPair ? mapa_rank(bar_tempty, 0) : bar_tempty;
 
-  if (warp < kProducerWarps) {
+  if (warp < kProd) {
     // ================================ A converters (raw smem -> hi/lo -> TMEM) ===========
     // group g = warp/8 takes chunks g, g+2, ...; inside a group warp w owns TMEM lane quarter w&3 (rows
     // 32*(w&3)+lane) and K-columns 16*((w>>2)&1).. of the chunk = four 16-byte pieces of its row in the raw
@@ -230,18 +240,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       while (mc >= kch) { mc -= kch; ++mtile; }
       const int64_t grow = tile_row0(group + (int64_t)mtile * n_groups) + row;
       const uint32_t w = grow < p.m ? __ldg(p.a_actmask + grow * kch + mc) : 0u;
-      mc += kConvGroups;
+      mc += kGroups;
       return w;
     };
     uint32_t mw = (kMasked && grp < total) ? load_mask_word() : 0u;
     long long c_rfull = 0, c_empty = 0, c_st = 0, c_total = TC_NOW();
     int s = grp;                    // TMEM stage of chunk `it` (it % n_stages) and the parity of this use of it
     uint32_t ph = 0;
-    for (int it = grp; it < total; it += kConvGroups) {
+    for (int it = grp; it < total; it += kGroups) {
       const int rs = it & (kRawStages - 1);                    // raw stage and the parity of this use of it
       const uint32_t rph = (uint32_t)(it / kRawStages) & 1u;
       const uint8_t* tile = sm_raw + (size_t)rs * kRawBytes;
-      const uint32_t mw_next = (kMasked && it + kConvGroups < total) ? load_mask_word() : 0u;
+      const uint32_t mw_next = (kMasked && it + kGroups < total) ? load_mask_word() : 0u;
       { TC_T0(); mbar_wait(bar_rfull + 8 * rs, rph); TC_ACC(c_rfull); }   // the TMA bytes of this chunk have landed
       if (TC_EXP(64)) __nanosleep(500);
       float vv[16];
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         }
         TC_ACC(c_st);
       }
-      s += kConvGroups;
+      s += kGroups;
       if (s >= p.n_stages) { s -= p.n_stages; ph ^= 1u; }
     }
     if (warp == 0 || warp == kConvGroupWarps) {
@@ -299,11 +309,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
     }
   } else if (warp < kMmaWarp) {
     // ================================ epilogue =========================================
-    const int ew = warp - kProducerWarps;        // 0..7
+    const int ew = warp - kProd;                 // 0..kEpi-1
     const int quarter = ew & 3;                  // == warp % 4: the TMEM lanes this warp may read
     const int half = ew >> 2;                    // owns 32-column chunks cc = half, half+2, ...
     // staging tile of this warp in the TMA SWIZZLE_128B layout: 16-byte piece c of row r at r*128 + ((c ^ (r&7))*16)
-    const uint32_t stg_tile = smem_u32(sm_stg + ew * kStgBytes);
+    const uint32_t stg_tile = smem_u32(sm_stg + ew * kStg);
     const uint32_t stg_row = stg_tile + (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     const int64_t mask_ld = (p.n + 7) / 8;
@@ -336,9 +346,93 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
         if ((bits >> lane) & 1u) {
           add_row = p.add_src + (int64_t)(rank0 + __popc(bits & ((1u << lane) - 1u))) * p.ld_add + slice * BN;
           // pull the lines this warp will add into L2 while the tile's MMAs are still running
-          for (int cc = half; cc < n_cc; cc += 2)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(add_row + cc * kEpiCols) : "memory");
+          if (kWide) {
+            for (int u = half; u < 2 * n_cc; u += kEpi / 4)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(add_row + u * 16) : "memory");
+          } else {
+            for (int cc = half; cc < n_cc; cc += 2)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(add_row + cc * kEpiCols) : "memory");
+          }
         }
+      }
+      if (kWide) {
+        // 16 epilogue warps: this one owns the 16-column units u = half, half + 4, ... of its lane quarter (two per tile
+        // at BN = 128) and a 32-row x 16-column staging tile in the TMA SWIZZLE_64B layout (piece c of row r at
+        // r*64 + ((c ^ ((r >> 1) & 3)) * 16)), stored through the 16-column-box tensor map (tmap_out2)
+        const int n_units = 2 * n_cc;
+        const uint32_t stg_row16 = stg_tile + (uint32_t)lane * 64u;
+        const uint32_t sw16 = (uint32_t)(lane >> 1) & 3u;
+        mbar_wait(bar_tfull + 8 * buf, ph);
+        tc_fence_after();
+        if (half >= n_units) {                           // narrow slices leave some warps without a unit: they still release
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          continue;
+        }
+        for (int u = half; u < n_units; u += kEpi / 4) {
+          const int lcol = u * 16;
+          const int col0 = slice * BN + lcol;
+          uint32_t v[16];
+          tmem_ld16(tmem_base + (uint32_t)(buf * BN + lcol) + ((uint32_t)(quarter * 32) << 16), v);
+          if (u + kEpi / 4 >= n_units) {                 // this warp's last read of the accumulator: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_after(bar_tempty + 8 * buf, v[0] | v[15]);
+          }
+          uint32_t act = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = *reinterpret_cast<const float4*>(sm_bias + lcol + 4 * q);
+            float x0 = __uint_as_float(v[4 * q + 0]), x1 = __uint_as_float(v[4 * q + 1]);
+            float x2 = __uint_as_float(v[4 * q + 2]), x3 = __uint_as_float(v[4 * q + 3]);
+            if (add_row != nullptr) {
+              const float4 av = __ldg(reinterpret_cast<const float4*>(add_row + lcol) + q);
+              x0 += av.x; x1 += av.y; x2 += av.z; x3 += av.w;
+            }
+            x0 = fmaxf(x0 + bq.x, relu_floor); x1 = fmaxf(x1 + bq.y, relu_floor);
+            x2 = fmaxf(x2 + bq.z, relu_floor); x3 = fmaxf(x3 + bq.w, relu_floor);
+            if (kDrop == 1) {
+              const uint2 w = dropout_block(row_key, (uint32_t)(col0 >> 2) + (uint32_t)q);
+              x0 = (w.x << 16) >= thr_hi ? x0 * p.dropout_scale : 0.f;
+              x1 = w.x >= thr_hi ? x1 * p.dropout_scale : 0.f;
+              x2 = (w.y << 16) >= thr_hi ? x2 * p.dropout_scale : 0.f;
+              x3 = w.y >= thr_hi ? x3 * p.dropout_scale : 0.f;
+            } else if (kDrop == 2) {
+              uint32_t mbits = 0;
+              if (row < p.m) {
+                const int c = col0 + 4 * q;                     // multiple of 4: the nibble of one byte
+                const uint32_t byte = __ldg(p.mask_bits + row * mask_ld + (c >> 3));
+                mbits = (c & 4) ? (byte & 0xFu) : (byte >> 4);   // MSB-first: bit 3 = first element
+              }
+              x0 = (mbits & 8u) ? x0 * p.dropout_scale : 0.f;
+              x1 = (mbits & 4u) ? x1 * p.dropout_scale : 0.f;
+              x2 = (mbits & 2u) ? x2 * p.dropout_scale : 0.f;
+              x3 = (mbits & 1u) ? x3 * p.dropout_scale : 0.f;
+            }
+            act |= ((x0 > 0.f ? 1u : 0u) | (x1 > 0.f ? 2u : 0u) | (x2 > 0.f ? 4u : 0u) | (x3 > 0.f ? 8u : 0u)) << (4 * q);
+            v[4 * q + 0] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
+            v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+          }
+          if (p.actmask_out != nullptr && row < p.m)     // this unit's 16 bits of the (row, 32-column) word
+            reinterpret_cast<uint16_t*>(p.actmask_out)[(row * (int64_t)(p.n >> 5) + (col0 >> 5)) * 2 + ((col0 >> 4) & 1)] =
+                (uint16_t)act;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read the tile
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_row16 + (((uint32_t)q ^ sw16) << 4)),
+                         "r"(v[4 * q]), "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                         : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmap_out2)),
+                         "r"(stg_tile), "r"(col0), "r"((int)(row0 + quarter * 32))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        continue;                                        // next tile
       }
       { TC_T0(); mbar_wait(bar_tfull + 8 * buf, ph); TC_ACC(e_tfull); }
       if (TC_EXP(128)) __nanosleep(500);
@@ -541,7 +635,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tensor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_tensor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                           int box_cols = tc::kChunkK) {
   static EncodeTiledFn encode = nullptr;
   if (encode == nullptr) {
     void* fn = nullptr;
@@ -554,10 +649,11 @@ static int make_tensor_map(CUtensorMap* map, const float* base, int64_t rows, in
   // fp32 [rows, cols] row-major with row pitch ld; box = 32 columns (128 bytes, the swizzle span) x box_rows rows
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)tc::kChunkK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};      // 32 columns = the 128-byte swizzle span; 16 = 64 bytes
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MPGNN_REQUIRE(r == CUDA_SUCCESS, MPGNN_ECUDA, "proj_tcgen05: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return MPGNN_OK;
@@ -666,6 +762,8 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   } else {
     MPGNN_PROPAGATE(make_tensor_map(&map_out, a.out, a.m, a.n, a.ldo, 32));
     map_out2 = map_out;
+    if (a.add_src != nullptr)       // the wide-epilogue forward stores 32-row x 16-column boxes
+      MPGNN_PROPAGATE(make_tensor_map(&map_out2, a.out, a.m, a.n, a.ldo, 32, 16));
   }
   auto launch = [&](auto kernel) -> int {
     // the opt-in limit is per function and process wide: always raise it to the device maximum, so that concurrent
@@ -698,9 +796,9 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
                       p.ld_add % 4 == 0 && al16(p.add_src),
                   MPGNN_ENOTSUP, "proj_tcgen05: the compact addend goes with the plain forward epilogue only");
     switch (p.dropout_mode) {
-      case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false, false, true>);
-      case 1: return launch(tc::gemm_rows_tc_kernel<1, false, false, false, true>);
-      default: return launch(tc::gemm_rows_tc_kernel<2, false, false, false, true>);
+      case 0: return launch(tc::gemm_rows_tc_kernel<0, false, false, false, true, true>);
+      case 1: return launch(tc::gemm_rows_tc_kernel<1, false, false, false, true, true>);
+      default: return launch(tc::gemm_rows_tc_kernel<2, false, false, false, true, true>);
     }
   }
   if (p.a_actmask != nullptr) {

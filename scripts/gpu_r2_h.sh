@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_tcgen05.py tests/test_gpu_parity.py -q -p no:cacheprovider -x > gpurun_out/r2h_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_tcgen05.py tests/test_gpu_parity.py tests/test_gpu_trainer.py -q -p no:cacheprovider -x > gpurun_out/r2h_pytest.log 2>&1
 echo "pytest exit: $?"; tail -3 gpurun_out/r2h_pytest.log
-timeout 600 python bench.py --no-e2e --no-cpu-baseline --no-candidates --steps 16 > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.err
+timeout 600 python bench.py --no-e2e --no-cpu-baseline --no-candidates --no-api --steps 16 > gpurun_out/r2h_bench.json 2> gpurun_out/r2h_bench.err
 echo "bench exit: $?"; tail -2 gpurun_out/r2h_bench.err
 python - <<'PY'
 import json
