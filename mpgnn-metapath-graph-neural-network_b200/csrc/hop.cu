@@ -122,13 +122,18 @@ int hop_fwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, int64_t f_in
     ScopedTimer tm("spmm_mean_fwd", s);
     MPGNN_PROPAGATE(launch_spmm_graph(g, rel, /*transpose=*/0, /*mean=*/1, x, f_in, f_in, nullptr, 0, h, f_in, s));
   }
-  MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp, w, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
-  MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp + f_in * f_out, root, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
+  // [W; root] as one [2 f_in, f_out] operand: callers that keep root right behind W (the trainer's parameter block) need
+  // no packing at all, the others get two device copies into the scratch
+  const bool stacked = root == w + f_in * f_out;
+  if (!stacked) {
+    MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp, w, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
+    MPGNN_CUDA_CHECK(cudaMemcpyAsync(bp + f_in * f_out, root, (size_t)(f_in * f_out) * 4, cudaMemcpyDeviceToDevice, s));
+  }
 
   GemmRowsArgs a{};
   a.a1 = h; a.lda1 = f_in; a.k1 = f_in;
   a.a2 = x; a.lda2 = f_in; a.k2 = f_in;
-  a.b = bp; a.m = g->n; a.n = f_out;
+  a.b = stacked ? w : bp; a.m = g->n; a.n = f_out;
   a.bias = bias;
   a.relu = (flags & MPGNN_F_RELU) ? 1 : 0;
   a.dropout_mode = drop_seed ? 1 : (drop_mask ? 2 : 0);
@@ -279,8 +284,12 @@ int hop_bwd(const mpgnn_graph_impl* g, int64_t rel, const float* x, const float*
     // [t | g_z root^T] = g_z @ [W^T | root^T], first f_in columns divided by deg_r(row).  The two halves go to two
     // tensors: t to the workspace, g_z root^T straight into g_x, so that the transposed aggregation runs in place
     // and touches only the rows of g_x that have incoming messages.
-    MPGNN_PROPAGATE(launch_pack_b(bp2, 2 * f_in, w, 1, f_out, f_out, f_in, s));
-    MPGNN_PROPAGATE(launch_pack_b(bp2 + f_in, 2 * f_in, root, 1, f_out, f_out, f_in, s));
+    if (root == w + f_in * f_out) {      // [W; root] contiguous: its transpose [W^T | root^T] in one launch
+      MPGNN_PROPAGATE(launch_pack_b(bp2, 2 * f_in, w, 1, f_out, f_out, 2 * f_in, s));
+    } else {
+      MPGNN_PROPAGATE(launch_pack_b(bp2, 2 * f_in, w, 1, f_out, f_out, f_in, s));
+      MPGNN_PROPAGATE(launch_pack_b(bp2 + f_in, 2 * f_in, root, 1, f_out, f_out, f_in, s));
+    }
     GemmRowsArgs a{};
     a.a1 = gz_src; a.lda1 = f_out; a.k1 = f_out;
     a.a2 = nullptr; a.lda2 = 0; a.k2 = 0;

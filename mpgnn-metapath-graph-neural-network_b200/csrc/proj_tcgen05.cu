@@ -63,7 +63,8 @@ constexpr int kMaxBBytes = 131072;                                // hi + lo of 
 struct Params {
   const float* a1; int64_t lda1; int k1;
   const float* a2; int64_t lda2; int k2;
-  const float* b_img;          // [n_slices][2][K*BN] floats: hi image then lo image, UMMA K-major layout
+  const float* b_raw;          // B [K, n] row-major (ld = n): every CTA splits ITS column slice into the hi / lo UMMA images
+                               // while it loads it -- no separate image-building launch in front of the GEMM
   int64_t m; int n; int bn; int n_slices;
   const float* bias;
   int relu;
@@ -101,22 +102,6 @@ __device__ unsigned long long g_tc_dbg[64];
 #define TC_ACC(var)
 #define TC_DUMP(role, k, v)
 #endif
-
-// Re-lays B[K,N] (row-major) into per-slice UMMA images: element (n,k) of a slice lives at byte
-// (n/8)*SBO + (k/4)*128 + (n%8)*16 + (k%4)*4 with SBO = (K/4)*128, split into hi and lo.
-__global__ void prep_b_images_kernel(const float* __restrict__ b, int k, int n, int bn, float* __restrict__ img) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)k * n) return;
-  const int kk = (int)(i / n), nn = (int)(i % n);
-  const int slice = nn / bn, nl = nn % bn;
-  const float v = b[i];
-  const float hi = tf32_hi(v);
-  const int64_t sbo_f = (int64_t)(k / 4) * 32;   // floats
-  const int64_t off = (int64_t)(nl / 8) * sbo_f + (int64_t)(kk / 4) * 32 + (nl % 8) * 4 + (kk % 4);
-  float* base = img + (int64_t)slice * 2 * k * bn;
-  base[off] = hi;
-  base[(int64_t)k * bn + off] = v - hi;
-}
 
 // kDrop: 0 none, 1 seeded, 2 mask bits; kDeg: divide the first deg_cols columns by deg; kMasked: gate A by a_actmask.
 // kPair: CTA pairs (clusters of 2, tcgen05 cta_group::2).  The pair owns a 256-row tile and a BN-column slice: each CTA
@@ -199,13 +184,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_rows_tc_kernel(const Params 
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  {  // resident B slice (already in UMMA layout in global memory): straight 16-byte copies
-    // images are laid out per BNB-column slice: [slice][hi | lo][K * BNB]; a pair's CTA `rank` takes half `rank`
-    const int img = kPair ? slice * 2 + (int)rank : slice;
-    const uint4* src = reinterpret_cast<const uint4*>(p.b_img + (int64_t)img * 2 * K * BNB);
-    uint4* dst = reinterpret_cast<uint4*>(sm_b_hi);
-    const int n16 = 2 * b_bytes / 16;
-    for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
+  {  // resident B slice: read raw (coalesced along n), split hi/lo, store in the UMMA K-major no-swizzle layout --
+     // element (n, k) of the slice at float offset (n/8)*SBO + (k/4)*32 + (n%8)*4 + (k%4), SBO = (K/4)*32
+    const int img = kPair ? slice * 2 + (int)rank : slice;       // BNB-column slice of B this CTA keeps
+    const float* src = p.b_raw + (int64_t)img * BNB;
+    float* hi_f = reinterpret_cast<float*>(sm_b_hi);
+    float* lo_f = reinterpret_cast<float*>(sm_b_lo);
+    const int sbo_f = (K / 4) * 32;
+    for (int i = tid; i < K * BNB; i += kThreads) {
+      const int kk = i / BNB, nl = i - kk * BNB;
+      const float v = __ldg(src + (int64_t)kk * p.n + nl);
+      const float hi = tf32_hi(v);
+      const int off = (nl >> 3) * sbo_f + (kk >> 2) * 32 + (nl & 7) * 4 + (kk & 3);
+      hi_f[off] = hi;
+      lo_f[off] = v - hi;
+    }
     if (tid < BN) sm_bias[tid] = (p.bias != nullptr) ? __ldg(p.bias + slice * BN + tid) : 0.f;
     fence_proxy_async();
   }
@@ -716,12 +709,11 @@ int launch_proj_tcgen05_ws(const GemmRowsArgs& a, uint32_t flags, float* b_img, 
   const int bnb = pair ? 64 : bn;              // B columns resident per CTA
   if (pair) bn = 128;
   const int n_slices = (int)(a.n / bn);
-  tc::prep_b_images_kernel<<<(unsigned)ceil_div(k * a.n, 256), 256, 0, s>>>(a.b, (int)k, (int)a.n, bnb, b_img);
-  MPGNN_LAUNCH_CHECK();
+  (void)b_img; (void)bnb;      // the images are built inside the kernel now; the scratch argument stays for the callers
   tc::Params p{};
   p.a1 = a.a1; p.lda1 = a.lda1; p.k1 = (int)a.k1;
   p.a2 = a.a2; p.lda2 = a.lda2; p.k2 = (int)a.k2;
-  p.b_img = b_img;
+  p.b_raw = a.b;
   p.m = a.m; p.n = (int)a.n; p.bn = bn; p.n_slices = n_slices;
   p.bias = a.bias; p.relu = a.relu;
   p.deg_ptr = a.deg_ptr; p.deg_cols = a.deg_ptr ? (int)a.deg_cols : 0;
