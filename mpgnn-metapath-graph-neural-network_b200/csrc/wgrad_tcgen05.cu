@@ -353,203 +353,6 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
   }
 }
 
-// ---- one 128-wide operand, g_z^T fed from TENSOR MEMORY ------------------------------------------------------------
-//   D^T[128 x 128] = g_z^T x      (x = the lone A operand: node features, or the compact h_c)
-// The two weight gradients of the compact hop.  Same split, same chunk-to-CTA assignment, same partial layout and the
-// same order of the three MMA terms as the shared-memory kernel above, but the M operand (g_z^T: lane = feature of
-// g_z, column = node row) goes registers -> TMEM with tcgen05.st instead of through a shared-memory tile:
-//  * every node row of g_z is read with coalesced 128-byte LDG.32 (warp = one 32-feature quarter of 8 rows), gated by
-//    the activation bitmask, split hi/lo and written to a ring of 64-column TMEM stages (hi | lo);
-//  * only x is staged in shared memory (hi/lo MN-major tiles, 32 KB per stage): per 32-row chunk the shared-memory
-//    traffic drops from 64 KB of stores + 96 KB of MMA operand reads to 32 KB + 48 KB, and the producers issue half
-//    the STS -- what was left between the 4.1 TB/s of the shared-memory kernel and the HBM rate of the projection
-//    kernel, which feeds its A operand the same way.
-constexpr int kStagesTs = 4;                       // x hi/lo tiles in shared memory, g_z hi|lo columns in TMEM
-constexpr int kTsStageBytes = 2 * kATileBytes;     // 32 KB
-constexpr int kTsACols = 2 * kRowsPerChunk;        // TMEM columns per stage: hi | lo
-constexpr int kTsTmemCols = 512;                   // 128 (accumulator) + 4 x 64 (stages), next power of two
-
-template <bool kMasked, int kPF>
-__global__ void __launch_bounds__(kThreadsW, 1) wgrad_ts_kernel(const ParamsW p) {
-  constexpr int N = kFeat;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesTs * kTsStageBytes);   // full[], empty[], done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStagesTs + 1);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kStagesTs);
-  const uint32_t bar_done = smem_u32(bars + 2 * kStagesTs);
-  const int64_t total_chunks = (p.m + kRowsPerChunk - 1) / kRowsPerChunk;
-  const int n_chunks = (int)(total_chunks > blockIdx.x ? (total_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
-  const int64_t r_end = p.m;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStagesTs; ++s) {
-      mbar_init(bar_full + 8 * s, kProducerWarpsW);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    mbar_init(bar_done, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == kMmaWarpW) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)kTsTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_a = tmem_base + (uint32_t)N;      // stage ring behind the accumulator
-
-  if (warp < kProducerWarpsW) {
-    // ================================ producers ==========================================
-    const int q = warp & 3, o = warp >> 2;               // TMEM lane quarter (32 features of g_z), 8-row slice of the chunk
-    const int gcol = q * 32 + lane;
-    int x_row[2], x_soff[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      x_row[u] = warp * 2 + u;                           // one fully coalesced 512-byte row of x per warp instruction
-      x_soff[u] = (int)mn_tile_offset16(lane, x_row[u], kFeat / 32);
-    }
-    const uint32_t my_ta = tmem_a + (uint32_t)(o * 8) + ((uint32_t)(q * 32) << 16);
-    float csum = 0.f;
-    float4 xb[kPF][2];
-    float gb[kPF][8];
-    uint32_t mb[kPF];
-    int pf = 0;
-    auto issue = [&](float4 (&xd)[2], float (&gd)[8], uint32_t& mw) {
-      const int64_t row0 = ((int64_t)pf * gridDim.x + blockIdx.x) * kRowsPerChunk;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int64_t ra = row0 + x_row[u];
-        xd[u] = ra < r_end ? __ldg(reinterpret_cast<const float4*>(p.a1 + ra * p.lda1 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const int64_t rg = row0 + o * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) gd[j] = rg + j < r_end ? __ldg(p.b + (rg + j) * p.ldb + gcol) : 0.f;
-      // lane l holds the mask word of row l % 8 of the slice (word q of the row's four); shuffled out at use
-      if (kMasked) mw = rg + (lane & 7) < r_end ? __ldg(p.b_actmask + (rg + (lane & 7)) * (N / 32) + q) : 0u;
-      ++pf;
-    };
-    auto store_x = [&](int s, const float4 (&xd)[2]) {
-      uint8_t* st = smem + (size_t)s * kTsStageBytes;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float4 v = xd[u];
-        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        *reinterpret_cast<float4*>(st + x_soff[u]) = h;
-        *reinterpret_cast<float4*>(st + kATileBytes + x_soff[u]) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-      }
-    };
-    auto store_g = [&](int s, const float (&gd)[8], uint32_t mw) {
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = gd[j];
-        if (kMasked) {                                   // fused ReLU/dropout backward: g_z = g_y gated by [y > 0]
-          const uint32_t w = __shfl_sync(0xFFFFFFFFu, mw, j);
-          v = ((w >> lane) & 1u) ? v * p.b_scale : 0.f;
-        }
-        csum += v;
-        const float h = tf32_hi(v);
-        hi[j] = __float_as_uint(h);
-        lo[j] = __float_as_uint(v - h);
-      }
-      const uint32_t ta = my_ta + (uint32_t)(s * kTsACols);
-      tmem_st8(ta, hi);
-      tmem_st8(ta + kRowsPerChunk, lo);
-    };
-#pragma unroll
-    for (int j = 0; j < kPF; ++j) {
-      mb[j] = 0u;
-      if (j < n_chunks) issue(xb[j], gb[j], mb[j]);
-    }
-    int s = 0;
-    uint32_t sph = 0;
-    for (int it0 = 0; it0 < n_chunks; it0 += kPF) {
-#pragma unroll
-      for (int j = 0; j < kPF; ++j) {
-        const int it = it0 + j;
-        if (it < n_chunks) {
-          mbar_wait(bar_empty + 8 * s, sph ^ 1u);          // the MMAs that read stage s (shared tiles and TMEM columns) are done
-          tc_fence_after();
-          store_x(s, xb[j]);
-          store_g(s, gb[j], mb[j]);
-          if (it + kPF < n_chunks) issue(xb[j], gb[j], mb[j]);   // registers are free again: next loads go out before the waits
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          fence_proxy_async();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_full + 8 * s);
-          if (++s == kStagesTs) { s = 0; sph ^= 1u; }
-        }
-      }
-    }
-    // column sums of g_z: slab row o of this CTA's [32][N] slab holds the 8-row slices' sums, the other rows are zero
-    float* slab = p.colsum_part + (int64_t)blockIdx.x * kRowsPerChunk * N;
-    slab[o * N + gcol] = csum;
-#pragma unroll
-    for (int r = 0; r < 7; ++r) slab[(4 + o * 7 + r) * N + gcol] = 0.f;
-  } else if (warp == kMmaWarpW) {
-    // ================================ MMA issuer ==========================================
-    // fp32 accumulate, tf32 x tf32, A from TMEM (K-major by construction), B MN-major
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
-                               ((uint32_t)(kFeat >> 4) << 24);
-    constexpr uint32_t x_sbo = (kFeat / 32) * 512;       // next group of 4 K-rows
-    const uint32_t s0 = smem_u32(smem);
-    int s = 0;
-    uint32_t sph = 0;
-    if (elect_one())
-    for (int it = 0; it < n_chunks; ++it) {
-      mbar_wait(bar_full + 8 * s, sph);
-      tc_fence_after();
-      const uint32_t st = s0 + (uint32_t)(s * kTsStageBytes);
-      const uint32_t ta = tmem_a + (uint32_t)(s * kTsACols);
-#pragma unroll
-      for (int kg = 0; kg < kRowsPerChunk / 8; ++kg) {
-        const uint32_t xo = kg * 2 * x_sbo;
-        const uint64_t xh = desc_mn(st + xo, x_sbo), xl = desc_mn(st + kATileBytes + xo, x_sbo);
-        umma_tf32_ts(tmem_base, ta + kg * 8, xh, idesc, (it | kg) != 0 ? 1u : 0u);
-        umma_tf32_ts(tmem_base, ta + kRowsPerChunk + kg * 8, xh, idesc, 1u);
-        umma_tf32_ts(tmem_base, ta + kg * 8, xl, idesc, 1u);
-      }
-      umma_commit(bar_empty + 8 * s);
-      if (it == n_chunks - 1) umma_commit(bar_done);
-      if (++s == kStagesTs) { s = 0; sph ^= 1u; }
-    }
-    __syncwarp();
-  } else {
-    // ================================ final epilogue: TMEM -> per-CTA partial =============
-    // D^T: lane = output column n (feature of g_z), TMEM column j = row of the gradient (feature of x)
-    const int ew = warp - kProducerWarpsW;
-    float* part = p.partials + (int64_t)blockIdx.x * 2 * kFeat * N;
-    const int mrow = ew * 32 + lane;
-    if (n_chunks > 0) {
-      mbar_wait(bar_done, 0);
-      tc_fence_after();
-    }
-    for (int cc = 0; cc < kFeat / 32; ++cc) {
-      uint32_t v[32];
-      if (n_chunks > 0) {
-        tmem_ld32(tmem_base + (uint32_t)(cc * 32) + ((uint32_t)(ew * 32) << 16), v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) part[(int64_t)(cc * 32 + i) * N + mrow] = __uint_as_float(v[i]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarpW) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTsTmemCols) : "memory");
-  }
-}
-
 // Fixed-order reduction of the per-CTA partials (and of the [grid][32][N] column-sum slabs).  One
 // warp per group of 32 consecutive outputs: lane l owns output 32*g + l; the `grid` partials are cut into
 // kRedSeg contiguous segments summed by kRedSeg warps of the block concurrently (coalesced 128-byte
@@ -651,24 +454,8 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   const bool stacked = a.k1 == tcw::kFeat / 2;
   const bool single = a.k1 == tcw::kFeat && a.k2 == 0;
   if (single) {
-    static const int exp_mode = getenv("MPGNN_WGRAD_EXP") ? atoi(getenv("MPGNN_WGRAD_EXP")) : 0;
-    auto launch_ts = [&](auto kernel) -> int {
-      const size_t smem_ts = (size_t)tcw::kStagesTs * tcw::kTsStageBytes + (2 * tcw::kStagesTs + 1) * 8 + 16;
-      MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-      kernel<<<grid, tcw::kThreadsW, smem_ts, s>>>(p);
-      MPGNN_LAUNCH_CHECK();
-      return MPGNN_OK;
-    };
-    if (exp_mode == 1) {
-      if (masked) MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, false, true>));
-      else MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, false, true>));
-    } else if (exp_mode == 2) {
-      if (masked) MPGNN_PROPAGATE(launch_ts(tcw::wgrad_ts_kernel<true, 3>));
-      else MPGNN_PROPAGATE(launch_ts(tcw::wgrad_ts_kernel<false, 3>));
-    } else {
-      if (masked) MPGNN_PROPAGATE(launch_ts(tcw::wgrad_ts_kernel<true, 2>));
-      else MPGNN_PROPAGATE(launch_ts(tcw::wgrad_ts_kernel<false, 2>));
-    }
+    if (masked) MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, false, true>));
+    else MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, false, true>));
   } else
   switch ((a.n == 128 ? 4 : 0) + (masked ? 2 : 0) + (stacked ? 1 : 0)) {
     case 0: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, false, false>)); break;

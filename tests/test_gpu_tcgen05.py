@@ -410,3 +410,28 @@ def test_compact_hop_kernel_classes_and_autograd_path():
     assert lib.mpgnn_hop_h_rows(graph.handle, 2, 128, 64, _lib.F_TF32X3 | _lib.F_COMPACT_H) == n      # no such wgrad shape
     assert lib.mpgnn_hop_h_rows(graph.handle, 2, 96, 128, _lib.F_TF32X3 | _lib.F_COMPACT_H) == n
     assert lib.mpgnn_hop_h_rows(graph.handle, 2, 128, 128, _lib.F_COMPACT_H) == n                     # fp32 (SIMT) path
+
+
+@pytest.mark.parametrize("m", [1, 31, 32, 33, 148 * 32 - 1, 148 * 32, 148 * 32 + 1, 100003])
+def test_gemm_tn_row_counts_around_chunk_and_cta_boundaries(m):
+    """out = A^T B and colsum(B) of the dense helper (the weight-gradient kernels: 32-row chunks dealt round-robin to
+    148 CTAs, fixed-order split-K) against a float64 product, at row counts on both sides of every boundary; twice into
+    NaN-filled outputs and scratch (no stale partial may be read, run-to-run bits identical)."""
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(m)
+    a = torch.randn(m, 128, device=DEV, generator=g)
+    b = torch.randn(m, 128, device=DEV, generator=g)
+    wsb = lib.mpgnn_gemm_workspace_bytes(m, 128, 128)
+    ref = a.double().t() @ b.double()
+    ref_cs = b.double().sum(0)
+    outs = []
+    for rep in range(2):
+        out = torch.full((128, 128), float("nan"), device=DEV)
+        cs = torch.full((128,), float("nan"), device=DEV)
+        ws = torch.full((wsb // 4,), float("nan"), device=DEV)
+        _lib.check(lib.mpgnn_gemm_tn(_lib.ptr(a), 128, m, 128, _lib.ptr(b), 128, 128, _lib.ptr(out), 128, _lib.ptr(cs),
+                                     _lib.ptr(ws), wsb, _lib.current_stream()))
+        torch.cuda.synchronize()
+        assert rel_err(out.double(), ref) <= TOL and rel_err(cs.double(), ref_cs) <= TOL
+        outs.append((out, cs))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
