@@ -28,11 +28,15 @@
 //    shared-memory layout the hardware accepts for MN-major tf32 operands; they also keep the
 //    running column sums of B in registers.
 //  * one warp issues the 24 MMAs of a chunk (4 K-steps x 2 accumulators x 3 terms).
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "tc_common.cuh"
 
 namespace mpgnn {
+
+// proj_tcgen05.cu: fp32 [rows, cols] row-major tensor map, box = box_cols x box_rows (32 columns: SWIZZLE_128B)
+int make_tensor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols);
 
 namespace tcw {
 
@@ -353,6 +357,243 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
   }
 }
 
+// ---- one 128-wide operand, TMA-fed, g_z^T in TENSOR MEMORY ---------------------------------------------------------
+//   D^T[128 x 128] = g_z^T x      (x = the lone A operand: node features, or the compact h_c)
+// The two weight gradients of the compact hop, built like the projection kernel (the one kernel family of this library
+// that streams at the HBM rate): nobody holds global loads in registers.
+//  * one thread streams 32-row chunks of g_z and x with TMA (4 + 4 boxes of 32 columns x 32 rows, SWIZZLE_128B, rows
+//    past M zero filled) and the chunk's activation-mask words with one bulk copy into a 4-deep raw ring (128 KB in
+//    flight per SM, twice what the register-staged producers of the kernel above could hold);
+//  * 16 converter warps read the raw tiles conflict-free: g_z transposed on the way (warp = 32 features x 8 rows, lane
+//    = feature: LDS.32 along the rows), gated by the mask, split hi/lo and tcgen05.st'ed into a ring of 64-column TMEM
+//    stages (lane = feature, column = node row); x row-wise (LDS.128), split into hi/lo MN-major UMMA tiles in shared
+//    memory.  They keep the column sums of g_z (one feature per thread);
+//  * one thread issues tcgen05.mma.kind::tf32 with A = g_z^T from TMEM, B = the x tiles: 3 MMAs per 8 rows, the same
+//    terms in the same order as the kernel above; same chunk-to-CTA assignment and partial layout, so the summation
+//    tree is still a function of the shape only.
+constexpr int kRawStagesT = 4;
+constexpr int kOpStagesT = 3;
+constexpr int kRawBytesT = 2 * kATileBytes;        // g_z boxes (16 KB) then x boxes (16 KB)
+constexpr int kOpBytesT = 2 * kATileBytes;         // x hi | x lo
+constexpr int kMaskBytesT = kRowsPerChunk * (kFeat / 32) * 4;      // 512
+constexpr int kTmaWarpT = kMmaWarpW + 1;           // 21
+constexpr int kThreadsT = (kTmaWarpT + 1) * 32;    // 704
+constexpr int kACOlsT = 2 * kRowsPerChunk;         // TMEM columns per stage: hi | lo
+constexpr int kTmemColsT = 512;                    // 128 (accumulator) + 3 x 64, next power of two
+constexpr int kBarsT = 2 * kRawStagesT + 2 * kOpStagesT + 1;
+constexpr size_t kSmemT = (size_t)kRawStagesT * (kRawBytesT + kMaskBytesT) + (size_t)kOpStagesT * kOpBytesT + kBarsT * 8 + 16;
+static_assert(kSmemT <= (size_t)kMaxDynSmem, "raw ring + operand ring exceed the shared memory of a CTA");
+
+template <bool kMasked>
+__global__ void __launch_bounds__(kThreadsT, 1) wgrad_tma_kernel(const ParamsW p, const __grid_constant__ CUtensorMap tmap_x,
+                                                                 const __grid_constant__ CUtensorMap tmap_g) {
+  constexpr int N = kFeat;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sm_raw = smem;
+  uint8_t* sm_op = smem + (size_t)kRawStagesT * kRawBytesT;
+  uint8_t* sm_mask = sm_op + (size_t)kOpStagesT * kOpBytesT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_mask + kRawStagesT * kMaskBytesT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBarsT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_rfull = smem_u32(bars), bar_rempty = bar_rfull + 8 * kRawStagesT;
+  const uint32_t bar_full = bar_rempty + 8 * kRawStagesT, bar_empty = bar_full + 8 * kOpStagesT;
+  const uint32_t bar_done = bar_empty + 8 * kOpStagesT;
+  const int64_t total_chunks = (p.m + kRowsPerChunk - 1) / kRowsPerChunk;
+  const int n_chunks = (int)(total_chunks > blockIdx.x ? (total_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+
+  if (tid == 0) {
+    for (int r = 0; r < kRawStagesT; ++r) {
+      mbar_init(bar_rfull + 8 * r, 1);                  // one arrive.expect_tx + the byte count of the copies
+      mbar_init(bar_rempty + 8 * r, kProducerWarpsW);
+    }
+    for (int s = 0; s < kOpStagesT; ++s) {
+      mbar_init(bar_full + 8 * s, kProducerWarpsW);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarpW) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kTmemColsT)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + (uint32_t)N;      // stage ring behind the accumulator
+
+  if (warp < kProducerWarpsW) {
+    // ================================ converters ==========================================
+    const int q = warp & 3, o = warp >> 2;               // TMEM lane quarter (32 features of g_z), 8-row slice of the chunk
+    // g_z: element (row o*8+j, feature q*32+lane) of box q; SWIZZLE_128B: 16-byte unit c of row r sits at c ^ (r % 8)
+    int g_off[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g_off[j] = q * 4096 + (o * 8 + j) * 128 + (((lane >> 2) ^ j) << 4) + (lane & 3) * 4;
+    // x: rows warp*2+u, lane = 16-byte unit of the 512-byte row = (box lane/8, unit lane%8)
+    int x_off[2], x_soff[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = warp * 2 + u;
+      x_off[u] = kATileBytes + (lane >> 3) * 4096 + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
+      x_soff[u] = (int)mn_tile_offset16(lane, r, kFeat / 32);
+    }
+    const uint32_t my_ta = tmem_a + (uint32_t)(o * 8) + ((uint32_t)(q * 32) << 16);
+    float csum = 0.f;
+    int rs = 0, s = 0;
+    uint32_t rph = 0, sph = 0;
+    for (int it = 0; it < n_chunks; ++it) {
+      const uint8_t* raw = sm_raw + (size_t)rs * kRawBytesT;
+      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(sm_mask + rs * kMaskBytesT) + (o * 8) * (N / 32) + q;
+      mbar_wait(bar_rfull + 8 * rs, rph);                 // the chunk's bytes have landed
+      float g[8];
+      uint32_t mw[8];
+      float4 xv[2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = *reinterpret_cast<const float*>(raw + g_off[j]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) xv[u] = *reinterpret_cast<const float4*>(raw + x_off[u]);
+      uint32_t dep = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mw[j] = kMasked ? mrow[j * (N / 32)] : 0xFFFFFFFFu;
+        dep |= __float_as_uint(g[j]) | mw[j];
+      }
+      dep |= __float_as_uint(xv[0].x) | __float_as_uint(xv[1].x);
+      // hand the raw stage back to the TMA thread only once every load above has delivered (see proj_tcgen05.cu: a
+      // plain arrive may overtake generic-proxy loads in flight and the refill would land under them)
+      dep = __reduce_or_sync(0xFFFFFFFFu, dep);
+      if (lane == 0) mbar_arrive_after(bar_rempty + 8 * rs, dep);
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = g[j];
+        if (kMasked) v = ((mw[j] >> lane) & 1u) ? v * p.b_scale : 0.f;   // fused ReLU/dropout backward: g_z = g_y gated by [y > 0]
+        csum += v;
+        const float h = tf32_hi(v);
+        hi[j] = __float_as_uint(h);
+        lo[j] = __float_as_uint(v - h);
+      }
+      mbar_wait(bar_empty + 8 * s, sph ^ 1u);             // the MMAs that read operand stage s (x tiles, TMEM columns) are done
+      tc_fence_after();
+      uint8_t* st = sm_op + (size_t)s * kOpBytesT;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 v = xv[u];
+        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        *reinterpret_cast<float4*>(st + x_soff[u]) = h;
+        *reinterpret_cast<float4*>(st + kATileBytes + x_soff[u]) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+      const uint32_t ta = my_ta + (uint32_t)(s * kACOlsT);
+      tmem_st8(ta, hi);
+      tmem_st8(ta + kRowsPerChunk, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      if (++rs == kRawStagesT) { rs = 0; rph ^= 1u; }
+      if (++s == kOpStagesT) { s = 0; sph ^= 1u; }
+    }
+    // column sums of g_z: slab row o of this CTA's [32][N] slab holds the 8-row slices' sums, the other rows are zero
+    float* slab = p.colsum_part + (int64_t)blockIdx.x * kRowsPerChunk * N;
+    const int gcol = q * 32 + lane;
+    slab[o * N + gcol] = csum;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) slab[(4 + o * 7 + r) * N + gcol] = 0.f;
+  } else if (warp == kTmaWarpT) {
+    // ================================ TMA producer (one lane) ============================
+    if (lane == 0) {
+      int rs = 0;
+      uint32_t rph = 0;
+      for (int it = 0; it < n_chunks; ++it) {
+        mbar_wait(bar_rempty + 8 * rs, rph ^ 1u);         // converters are done with this raw stage
+        const int64_t row0 = ((int64_t)it * gridDim.x + blockIdx.x) * kRowsPerChunk;
+        const int64_t rows = p.m - row0 < kRowsPerChunk ? p.m - row0 : kRowsPerChunk;
+        const uint32_t dst = smem_u32(sm_raw + (size_t)rs * kRawBytesT);
+        const uint32_t bar = bar_rfull + 8 * rs;
+        const uint32_t mask_bytes = kMasked ? (uint32_t)rows * (N / 32) * 4 : 0u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kRawBytesT + mask_bytes) : "memory");
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(dst + b * 4096), "l"(reinterpret_cast<uint64_t>(&tmap_g)), "r"(bar), "r"(b * 32), "r"((int)row0)
+              : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(dst + kATileBytes + b * 4096), "l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(bar), "r"(b * 32), "r"((int)row0)
+              : "memory");
+        }
+        if (kMasked)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(sm_mask + rs * kMaskBytesT)), "l"(p.b_actmask + row0 * (N / 32)), "r"(mask_bytes), "r"(bar)
+                       : "memory");
+        if (++rs == kRawStagesT) { rs = 0; rph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarpW) {
+    // ================================ MMA issuer ==========================================
+    // fp32 accumulate, tf32 x tf32, A from TMEM (K-major by construction), B MN-major
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                               ((uint32_t)(kFeat >> 4) << 24);
+    constexpr uint32_t x_sbo = (kFeat / 32) * 512;       // next group of 4 K-rows
+    const uint32_t s0 = smem_u32(sm_op);
+    int s = 0;
+    uint32_t sph = 0;
+    if (elect_one())
+    for (int it = 0; it < n_chunks; ++it) {
+      mbar_wait(bar_full + 8 * s, sph);
+      tc_fence_after();
+      const uint32_t st = s0 + (uint32_t)(s * kOpBytesT);
+      const uint32_t ta = tmem_a + (uint32_t)(s * kACOlsT);
+#pragma unroll
+      for (int kg = 0; kg < kRowsPerChunk / 8; ++kg) {
+        const uint32_t xo = kg * 2 * x_sbo;
+        const uint64_t xh = desc_mn(st + xo, x_sbo), xl = desc_mn(st + kATileBytes + xo, x_sbo);
+        umma_tf32_ts(tmem_base, ta + kg * 8, xh, idesc, (it | kg) != 0 ? 1u : 0u);
+        umma_tf32_ts(tmem_base, ta + kRowsPerChunk + kg * 8, xh, idesc, 1u);
+        umma_tf32_ts(tmem_base, ta + kg * 8, xl, idesc, 1u);
+      }
+      umma_commit(bar_empty + 8 * s);
+      if (it == n_chunks - 1) umma_commit(bar_done);
+      if (++s == kOpStagesT) { s = 0; sph ^= 1u; }
+    }
+    __syncwarp();
+  } else {
+    // ================================ final epilogue: TMEM -> per-CTA partial =============
+    // D^T: lane = output column n (feature of g_z), TMEM column j = row of the gradient (feature of x)
+    const int ew = warp - kProducerWarpsW;
+    float* part = p.partials + (int64_t)blockIdx.x * 2 * kFeat * N;
+    const int mrow = ew * 32 + lane;
+    if (n_chunks > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+    }
+    for (int cc = 0; cc < kFeat / 32; ++cc) {
+      uint32_t v[32];
+      if (n_chunks > 0) {
+        tmem_ld32(tmem_base + (uint32_t)(cc * 32) + ((uint32_t)(ew * 32) << 16), v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) part[(int64_t)(cc * 32 + i) * N + mrow] = __uint_as_float(v[i]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarpW) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemColsT) : "memory");
+  }
+}
+
 // Fixed-order reduction of the per-CTA partials (and of the [grid][32][N] column-sum slabs).  One
 // warp per group of 32 consecutive outputs: lane l owns output 32*g + l; the `grid` partials are cut into
 // kRedSeg contiguous segments summed by kRedSeg warps of the block concurrently (coalesced 128-byte
@@ -453,7 +694,21 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   const bool masked = a.b_actmask != nullptr;
   const bool stacked = a.k1 == tcw::kFeat / 2;
   const bool single = a.k1 == tcw::kFeat && a.k2 == 0;
-  if (single) {
+  static const int exp_mode = getenv("MPGNN_WGRAD_EXP") ? atoi(getenv("MPGNN_WGRAD_EXP")) : 0;
+  if (single && exp_mode != 1) {
+    MPGNN_REQUIRE(!masked || al16(a.b_actmask), MPGNN_EINVAL, "wgrad_tcgen05: activation mask must be 16-byte aligned");
+    CUtensorMap map_x, map_g;
+    MPGNN_PROPAGATE(make_tensor_map(&map_x, a.a1, a.m, tcw::kFeat, a.lda1, tcw::kRowsPerChunk, 32));
+    MPGNN_PROPAGATE(make_tensor_map(&map_g, a.b, a.m, tcw::kFeat, a.ldb, tcw::kRowsPerChunk, 32));
+    auto launch_t = [&](auto kernel) -> int {
+      MPGNN_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      kernel<<<grid, tcw::kThreadsT, tcw::kSmemT, s>>>(p, map_x, map_g);
+      MPGNN_LAUNCH_CHECK();
+      return MPGNN_OK;
+    };
+    if (masked) MPGNN_PROPAGATE(launch_t(tcw::wgrad_tma_kernel<true>));
+    else MPGNN_PROPAGATE(launch_t(tcw::wgrad_tma_kernel<false>));
+  } else if (single) {
     if (masked) MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, false, true>));
     else MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, false, true>));
   } else

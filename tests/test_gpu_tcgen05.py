@@ -325,7 +325,7 @@ def _relation_rows(graph, rel):
 
 
 @pytest.mark.parametrize("n,f_in,f_out,rel", [(40000, 128, 128, 1), (40000, 128, 128, 0), (25000, 64, 64, 1), (30001, 64, 128, 2),
-                                              (6000, 128, 128, 3)])
+                                              (6000, 128, 128, 3), (4737, 128, 128, 1), (4767, 128, 128, 0)])
 def test_compact_hop_matches_dense_hop_and_oracle(n, f_in, f_out, rel):
     from mpgnn_b200.mp_rgcn_layer import pack_mask_bits
     lib = _lib.load()
@@ -414,9 +414,10 @@ def test_compact_hop_kernel_classes_and_autograd_path():
 
 @pytest.mark.parametrize("m", [1, 31, 32, 33, 148 * 32 - 1, 148 * 32, 148 * 32 + 1, 100003])
 def test_gemm_tn_row_counts_around_chunk_and_cta_boundaries(m):
-    """out = A^T B and colsum(B) of the dense helper (the weight-gradient kernels: 32-row chunks dealt round-robin to
-    148 CTAs, fixed-order split-K) against a float64 product, at row counts on both sides of every boundary; twice into
-    NaN-filled outputs and scratch (no stale partial may be read, run-to-run bits identical)."""
+    """out = A^T B and colsum(B) of the dense helper (fixed-order split over the rows) against a float64 product, at row
+    counts on both sides of the 32-row and 148-CTA boundaries; twice into NaN-filled outputs and scratch (no stale
+    partial may be read, run-to-run bits identical).  The tensor-core weight gradients see the same row counts through
+    the compact-hop cases above (n = 4737, 4767, 6000)."""
     lib = _lib.load()
     g = torch.Generator(device=DEV).manual_seed(m)
     a = torch.randn(m, 128, device=DEV, generator=g)
