@@ -28,6 +28,11 @@
 //    shared-memory layout the hardware accepts for MN-major tf32 operands; they also keep the
 //    running column sums of B in registers.
 //  * one warp issues the 24 MMAs of a chunk (4 K-steps x 2 accumulators x 3 terms).
+//
+// ONE 128-wide operand with N = 128 (the compact hop: x^T g_z over all rows, h_c^T g_z over the rows with edges) runs
+// wgrad_tma_kernel further down instead: operands streamed by TMA into a raw ring, g_z^T transposed into TENSOR MEMORY
+// by the converter warps, only x staged as MMA tiles in shared memory -- 0.86 / 0.99 of the HBM floor at C4 where the
+// register-staged producers above reach 0.61.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -45,7 +50,6 @@ using namespace tc;
 constexpr int kRowsPerChunk = 32;                 // node rows (MMA K) per pipeline stage
 constexpr int kFeat = 128;                        // feature width of A1 / A2 (MMA M)
 constexpr int kStagesPair = 2;                     // two A operands: 96 KB per stage
-constexpr int kStagesSingle = 3;                   // one A operand: 64 KB per stage
 constexpr int kProducerWarpsW = 16;
 constexpr int kEpiWarpsW = 4;
 constexpr int kMmaWarpW = kProducerWarpsW + kEpiWarpsW;           // 20
@@ -90,19 +94,14 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t sbo) {
 
 // N = width of B (64 or 128); kMasked: B is gated by the activation bitmask; kStacked: A1, A2 are 64 wide and share
 // one 128-wide operand tile / one accumulator
-// kSingle (swapped roles only): ONE 128-wide A operand (the compact hop: x^T g_z over all rows, h_c^T g_z over the rows
-// with edges) -- the N operand is 128 wide, half the tile, half the MMA work
-template <int N, bool kMasked, bool kStacked, bool kSingle = false>
+// (ONE 128-wide A operand -- the compact hop -- has its own kernel below: wgrad_tma_kernel)
+template <int N, bool kMasked, bool kStacked>
 __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p) {
   constexpr bool kSwap = (N == 128) && !kStacked;      // g_z^T as the M operand, [h | x] as one N = 256 operand
-  static_assert(!kSingle || kSwap, "single-operand variant exists for the swapped 128-wide shape only");
-  constexpr int kHxWidth = kSingle ? kFeat : 2 * kFeat;   // width of the [h | x] (or lone) N operand
-  // a lone operand needs 64 KB per stage instead of 96: three stages fit, and the producers (what bounds this kernel)
-  // get one more chunk of slack against the MMA warp
-  constexpr int kStagesW = kSingle ? kStagesSingle : kStagesPair;
-  constexpr int kAOps = kSingle ? 1 : 2;                  // A operands staged per chunk
-  constexpr int kLoOff = kSingle ? kATileBytes : 2 * kATileBytes;    // swapped roles: lo image of the [h | x] tile
-  constexpr int kBOff = 2 * kAOps * kATileBytes;          // B tiles follow the A tiles
+  constexpr int kHxWidth = 2 * kFeat;                  // width of the [h | x] N operand
+  constexpr int kStagesW = kStagesPair;
+  constexpr int kLoOff = 2 * kATileBytes;              // swapped roles: lo image of the [h | x] tile
+  constexpr int kBOff = 4 * kATileBytes;               // B tiles follow the A tiles
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b_tile_bytes = kRowsPerChunk * N * 4;                    // one of hi / lo
   const int stage_bytes = kBOff + 2 * b_tile_bytes;                  // a1 hi/lo, (a2 hi/lo,) b hi/lo
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
     // swapped roles: one [h | x] tile of 8 MN atoms (hi @0, lo @32K); x goes to atoms 4-7 = 16-byte units 32..63
     int a2_soff[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) a2_soff[u] = (kSwap && !kSingle) ? (int)mn_tile_offset16(lane + 32, a_row[u], 2 * kFeat / 32) : a_soff[u];
+    for (int u = 0; u < 2; ++u) a2_soff[u] = kSwap ? (int)mn_tile_offset16(lane + 32, a_row[u], 2 * kFeat / 32) : a_soff[u];
     int b_row[2], b_col[2], b_soff[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -191,7 +190,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
           dst[2 + u] = z;
         } else {
           dst[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a1 + ra * p.lda1 + a_col[u])) : z;
-          dst[2 + u] = (ok && !kSingle) ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
+          dst[2 + u] = ok ? __ldg(reinterpret_cast<const float4*>(p.a2 + ra * p.lda2 + a_col[u])) : z;
         }
         const int64_t rb = row0 + b_row[u];
         dst[4 + u] = (u < n_units_b && rb < r_end) ? __ldg(reinterpret_cast<const float4*>(p.b + rb * p.ldb + b_col[u])) : z;
@@ -210,8 +209,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const ParamsW p)
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         if (kSwap) {
-          split_store(st + a_soff[u], kLoOff, src[u]);                             // [h | x] tile: hi @0, lo @32K (lone: @16K)
-          if (!kSingle) split_store(st + a2_soff[u], kLoOff, src[2 + u]);
+          split_store(st + a_soff[u], kLoOff, src[u]);                             // [h | x] tile: hi @0, lo @32K
+          split_store(st + a2_soff[u], kLoOff, src[2 + u]);
         } else {
           split_store(st + a_soff[u], kATileBytes, src[u]);                        // a1: hi @0, lo @16K
           if (!kStacked) split_store(st + 2 * kATileBytes + a_soff[u], kATileBytes, src[2 + u]);   // a2: hi @32K, lo @48K
@@ -677,10 +676,8 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   p.b_actmask = a.b_actmask; p.b_scale = a.b_scale;
   p.partials = ws;
   p.colsum_part = ws + (int64_t)grid * 2 * tcw::kFeat * a.n;
-  const bool single_op = a.k1 == tcw::kFeat && a.k2 == 0;
-  const int n_stages = single_op ? tcw::kStagesSingle : tcw::kStagesPair;
-  const size_t smem = (size_t)n_stages * ((single_op ? 2 : 4) * tcw::kATileBytes + 2 * tcw::kRowsPerChunk * a.n * 4) +
-                      (2 * n_stages + 1) * 8 + 16;
+  const int n_stages = tcw::kStagesPair;
+  const size_t smem = (size_t)n_stages * (4 * tcw::kATileBytes + 2 * tcw::kRowsPerChunk * a.n * 4) + (2 * n_stages + 1) * 8 + 16;
   auto launch = [&](auto kernel) -> int {
     // the opt-in limit is per function and process wide: always raise it to the device maximum, so that concurrent
     // launches of the same kernel with different tile sizes (candidate trainers on several host threads) cannot
@@ -694,8 +691,7 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
   const bool masked = a.b_actmask != nullptr;
   const bool stacked = a.k1 == tcw::kFeat / 2;
   const bool single = a.k1 == tcw::kFeat && a.k2 == 0;
-  static const int exp_mode = getenv("MPGNN_WGRAD_EXP") ? atoi(getenv("MPGNN_WGRAD_EXP")) : 0;
-  if (single && exp_mode != 1) {
+  if (single) {
     MPGNN_REQUIRE(!masked || al16(a.b_actmask), MPGNN_EINVAL, "wgrad_tcgen05: activation mask must be 16-byte aligned");
     CUtensorMap map_x, map_g;
     MPGNN_PROPAGATE(make_tensor_map(&map_x, a.a1, a.m, tcw::kFeat, a.lda1, tcw::kRowsPerChunk, 32));
@@ -708,9 +704,6 @@ int launch_wgrad_tcgen05(const GemmTnArgs& a, float* ws, cudaStream_t s) {
     };
     if (masked) MPGNN_PROPAGATE(launch_t(tcw::wgrad_tma_kernel<true>));
     else MPGNN_PROPAGATE(launch_t(tcw::wgrad_tma_kernel<false>));
-  } else if (single) {
-    if (masked) MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, true, false, true>));
-    else MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<128, false, false, true>));
   } else
   switch ((a.n == 128 ? 4 : 0) + (masked ? 2 : 0) + (stacked ? 1 : 0)) {
     case 0: MPGNN_PROPAGATE(launch(tcw::wgrad_tc_kernel<64, false, false>)); break;
