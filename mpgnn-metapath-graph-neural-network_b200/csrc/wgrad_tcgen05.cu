@@ -377,7 +377,7 @@ constexpr int kOpBytesT = 2 * kATileBytes;         // x hi | x lo
 constexpr int kMaskBytesT = kRowsPerChunk * (kFeat / 32) * 4;      // 512
 constexpr int kTmaWarpT = kMmaWarpW + 1;           // 21
 constexpr int kThreadsT = (kTmaWarpT + 1) * 32;    // 704
-constexpr int kACOlsT = 2 * kRowsPerChunk;         // TMEM columns per stage: hi | lo
+constexpr int kAColsT = 2 * kRowsPerChunk;         // TMEM columns per stage: hi | lo
 constexpr int kTmemColsT = 512;                    // 128 (accumulator) + 3 x 64, next power of two
 constexpr int kBarsT = 2 * kRawStagesT + 2 * kOpStagesT + 1;
 constexpr size_t kSmemT = (size_t)kRawStagesT * (kRawBytesT + kMaskBytesT) + (size_t)kOpStagesT * kOpBytesT + kBarsT * 8 + 16;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) wgrad_tma_kernel(const ParamsW p
         *reinterpret_cast<float4*>(st + x_soff[u]) = h;
         *reinterpret_cast<float4*>(st + kATileBytes + x_soff[u]) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
-      const uint32_t ta = my_ta + (uint32_t)(s * kACOlsT);
+      const uint32_t ta = my_ta + (uint32_t)(s * kAColsT);
       tmem_st8(ta, hi);
       tmem_st8(ta + kRowsPerChunk, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(kThreadsT, 1) wgrad_tma_kernel(const ParamsW p
       mbar_wait(bar_full + 8 * s, sph);
       tc_fence_after();
       const uint32_t st = s0 + (uint32_t)(s * kOpBytesT);
-      const uint32_t ta = tmem_a + (uint32_t)(s * kACOlsT);
+      const uint32_t ta = tmem_a + (uint32_t)(s * kAColsT);
 #pragma unroll
       for (int kg = 0; kg < kRowsPerChunk / 8; ++kg) {
         const uint32_t xo = kg * 2 * x_sbo;
